@@ -1,0 +1,367 @@
+// Sparse convolution on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   out[o, :] = Σ_k  in[nbr[k, o], :] @ W[k]           (output-stationary implicit GEMM)
+//
+// One persistent CTA per SM walks 128-row output tiles.  Warp roles:
+//   warps 0-3  gather: for every (offset k, 64-channel block) load the neighbour rows of the tile from HBM/L2
+//              (coalesced 16-byte loads, 16 lanes per 256-byte row segment), optionally apply the fused
+//              BatchNorm affine + activation of the producing layer, split fp32 → bf16 hi (+ lo), and store the
+//              128x64 tile into shared memory in the 128-byte-swizzled K-major UMMA layout.  Lane 0 of warp 0
+//              also streams the pre-swizzled weight slice W[k] with one bulk async copy (UBLKCP).
+//   warp  8    one elected thread issues tcgen05.mma (M=128, N=Cout, K=16) into a TMEM accumulator and
+//              commits to the stage's "empty" mbarrier; the accumulator is double-buffered in TMEM so the
+//              epilogue of tile t overlaps the main loop of tile t+1.
+//   warps 4-7  epilogue: tcgen05.ld the accumulator (lane = output row), add bias, store fp32 rows.
+// No atomics: every output row is written exactly once, results are run-to-run deterministic.
+//
+// precision 3 (the "fp32" mode): operands split as x = hi + lo (bf16 each) and three MMAs
+// hi·hi + lo·hi + hi·lo accumulate in fp32 — ~2^-16 relative error, well inside the 1e-3 parity bound.
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace pasco;
+using namespace umma;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int KBLK = 64;                    // channels per K-block (= one 128-byte swizzle row of bf16)
+constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB
+constexpr int NUM_GATHER_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_THREADS = (NUM_GATHER_WARPS + NUM_EPI_WARPS + 1) * 32;  // 288
+constexpr int MAX_STAGES = 8;
+
+struct ConvParams {
+  const float* in;
+  const int32_t* nbr;  // [K, n_out] or nullptr (identity)
+  const uint8_t* wpk;  // packed weights
+  const float* bias;
+  const float* in_scale;
+  const float* in_shift;
+  float* out;
+  int64_t n_out;
+  int64_t out_pitch;
+  int K, Cin, Cout, in_act;
+  int stages, tmem_cols;
+  int koff[32];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 [K, Cin, Cout] → per (k, kb): [hi image | lo image], image = N rows x 128 B, swizzled
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_pack_weights(const float* __restrict__ W, int K, int Cin, int Cout, int transpose,
+                               uint8_t* __restrict__ packed) {
+  const int N = transpose ? Cin : Cout;   // B rows
+  const int Kc = transpose ? Cout : Cin;  // contraction length
+  const int KB = Kc / KBLK;
+  int64_t total = (int64_t)K * KB * N * 8;  // one thread per 16-byte chunk (8 bf16)
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(t & 7);
+    int64_t r = t >> 3;
+    int n = (int)(r % N);
+    r /= N;
+    int kb = (int)(r % KB);
+    int k = (int)(r / KB);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int kc = kb * KBLK + c * 8 + j;
+      v[j] = transpose ? __ldg(W + ((int64_t)k * Cin + n) * Cout + kc) : __ldg(W + ((int64_t)k * Cin + kc) * Cout + n);
+    }
+    uint4 hi, lo;
+    uint2 h0, l0, h1, l1;
+    split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+    split4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    int64_t tile = ((int64_t)k * KB + kb) * (int64_t)N * 256;  // hi image then lo image
+    int64_t off = (int64_t)n * 128 + ((c ^ (n & 7)) << 4);
+    *reinterpret_cast<uint4*>(packed + tile + off) = hi;
+    *reinterpret_cast<uint4*>(packed + tile + (int64_t)N * 128 + off) = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float z, int act) {
+  if (act == 1) return fmaxf(z, 0.f);
+  if (act == 2) return z > 0.f ? z : 0.01f * z;
+  return z;
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: stages x [A_hi | A_lo? | B_hi | B_lo?], then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_tile = p.Cout * 128;
+  const int n_op = (NSPLIT == 3) ? 2 : 1;
+  const int stage_bytes = n_op * (A_TILE_BYTES + b_tile);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                      // [stages]
+  uint64_t* empty_bar = bars + MAX_STAGES;        // [stages]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.Cin / KBLK;
+  const int64_t num_tiles = (p.n_out + BLOCK_M - 1) / BLOCK_M;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(full_bar + s), NUM_GATHER_WARPS + 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(tfull_bar + b), 1);
+      mbar_init(smem_u32(tempty_bar + b), NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NUM_GATHER_WARPS) {
+    // ===================================== gather producers =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int chunk = lane & 15;   // 16-byte fp32 chunk inside the 64-channel block
+    const int rsub = lane >> 4;    // which of the 2 rows this half-warp handles per step
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * BLOCK_M + warp * 32;
+      for (int k = 0; k < p.K; ++k) {
+        int64_t my_row = row0 + lane;
+        int idx = -1;
+        if (my_row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + my_row) : (int)my_row;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          if (warp == 0 && lane == 0) {
+            const uint32_t bytes = (uint32_t)(n_op * b_tile);
+            mbar_arrive_expect_tx(smem_u32(full_bar + stage), bytes);
+            const uint8_t* src = p.wpk + ((int64_t)p.koff[k] * KB + kb) * (int64_t)p.Cout * 256;
+            bulk_g2s(smem_u32(st + n_op * A_TILE_BYTES), src, bytes, smem_u32(full_bar + stage));
+          }
+          const int cbase = kb * KBLK + chunk * 4;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool affine = p.in_scale != nullptr;
+          if (affine) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + cbase));
+            sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + cbase));
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 v[8];
+            int srcs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              int r = (half * 8 + i) * 2 + rsub;
+              srcs[i] = __shfl_sync(0xffffffffu, idx, r);
+              v[i] = srcs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)srcs[i] * p.Cin + cbase))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              int r = (half * 8 + i) * 2 + rsub;
+              float4 x = v[i];
+              if (affine || p.in_act) {
+                if (srcs[i] >= 0) {
+                  x.x = act_apply(fmaf(x.x, sc.x, sh.x), p.in_act);
+                  x.y = act_apply(fmaf(x.y, sc.y, sh.y), p.in_act);
+                  x.z = act_apply(fmaf(x.z, sc.z, sh.z), p.in_act);
+                  x.w = act_apply(fmaf(x.w, sc.w, sh.w), p.in_act);
+                }
+              }
+              const int trow = warp * 32 + r;
+              const uint32_t off = (uint32_t)trow * 128u + (uint32_t)(((chunk >> 1) ^ (trow & 7)) << 4) + (uint32_t)((chunk & 1) << 3);
+              uint2 hi, lo;
+              split4(x, hi, lo);
+              *reinterpret_cast<uint2*>(st + off) = hi;
+              if (NSPLIT == 3) *reinterpret_cast<uint2*>(st + A_TILE_BYTES + off) = lo;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.Cout, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(tempty_bar + buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.Cout);
+        uint32_t accum = 0;
+        for (int k = 0; k < p.K; ++k) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(smem_u32(full_bar + stage), phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
+            const uint32_t b_hi = st + n_op * A_TILE_BYTES, b_lo = b_hi + b_tile;
+#pragma unroll
+            for (int j = 0; j < KBLK / 16; ++j) {
+              const uint64_t da_hi = make_desc_sw128(a_hi + j * 32, 16, 1024);
+              const uint64_t db_hi = make_desc_sw128(b_hi + j * 32, 16, 1024);
+              mma_bf16(d_tmem, da_hi, db_hi, idesc, accum);
+              accum = 1;
+              if (NSPLIT == 3) {
+                const uint64_t da_lo = make_desc_sw128(a_lo + j * 32, 16, 1024);
+                const uint64_t db_lo = make_desc_sw128(b_lo + j * 32, 16, 1024);
+                mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
+                mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+              }
+            }
+            mma_commit(smem_u32(empty_bar + stage));
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        mma_commit(smem_u32(tfull_bar + buf));
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp - NUM_GATHER_WARPS;  // == warp % 4: TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(smem_u32(tfull_bar + buf), (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = tile * BLOCK_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.Cout);
+      float* orow = p.out + row * p.out_pitch;
+      int c0 = 0;
+      for (; c0 + 32 <= p.Cout; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (row < p.n_out) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.bias) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+      }
+      if (c0 < p.Cout) {  // 16-column tail (Cout % 32 == 16)
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (row < p.n_out) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.bias) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v <<= 1;
+  return v;
+}
+
+}  // namespace
+
+extern "C" int64_t pasco_conv_packed_bytes(int32_t K, int32_t Cin, int32_t Cout) {
+  return (int64_t)K * Cin * Cout * 4;
+}
+
+extern "C" int pasco_conv_pack_weights(const float* W, int32_t K, int32_t Cin, int32_t Cout, int32_t transpose,
+                                       void* packed, pasco_stream_t s) {
+  const int N = transpose ? Cin : Cout, Kc = transpose ? Cout : Cin;
+  PASCO_CHECK_ARG(Kc % KBLK == 0, "pasco_conv_pack_weights: contraction channels (%d) must be a multiple of 64", Kc);
+  PASCO_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256, "pasco_conv_pack_weights: output channels (%d) must be a multiple of 16 in [16,256]", N);
+  int64_t total = (int64_t)K * (Kc / KBLK) * N * 8;
+  k_pack_weights<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(W, K, Cin, Cout, transpose, (uint8_t*)packed);
+  PASCO_CHECK_LAUNCH("pasco_conv_pack_weights");
+  return 0;
+}
+
+extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
+                                     int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map,
+                                     const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
+                                     double* stats, float* out, int32_t precision, pasco_stream_t s) {
+  PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_forward_tc: precision must be 1 (bf16) or 3 (bf16x3)");
+  PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_tc: Cin (%d) must be a multiple of 64", Cin);
+  PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_tc: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
+  PASCO_CHECK_ARG(K >= 1 && K <= 32, "pasco_conv_forward_tc: K (%d) out of range", K);
+  PASCO_CHECK_ARG(stats == nullptr, "pasco_conv_forward_tc: fused output statistics are not implemented yet");
+  PASCO_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)packed_w) & 15) == 0, "pasco_conv_forward_tc: pointers must be 16-byte aligned");
+  (void)n_in;
+  if (n_out == 0) return 0;
+  int dev = 0, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int n_op = precision == 3 ? 2 : 1;
+  const int stage_bytes = n_op * (A_TILE_BYTES + Cout * 128);
+  const int fixed = 1024 /*align slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
+  int stages = (smem_optin - fixed) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  PASCO_CHECK_ARG(stages >= 2, "pasco_conv_forward_tc: not enough shared memory for 2 stages (Cout=%d)", Cout);
+  ConvParams p;
+  p.in = in; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w; p.bias = bias;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.out = out;
+  p.n_out = n_out; p.out_pitch = Cout;
+  p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
+  p.stages = stages; p.tmem_cols = pow2_cols(2 * Cout);
+  for (int k = 0; k < 32; ++k) p.koff[k] = (k < K) ? (koff_map ? koff_map[k] : k) : 0;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  int64_t tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
+  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  cudaError_t e;
+  if (precision == 3) {
+    e = cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_conv_tc<3><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_conv_tc<1><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("pasco_conv_forward_tc: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
+    return -1;
+  }
+  PASCO_CHECK_LAUNCH("pasco_conv_forward_tc");
+  return 0;
+}

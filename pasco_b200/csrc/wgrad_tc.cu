@@ -1,0 +1,308 @@
+// Weight gradient of the sparse convolution on tcgen05 (sm_100a).
+//
+//   dW[k] = Σ_o in[nbr[k,o], :]^T @ gout[o, :]
+//
+// UMMA view: D[M = 128 input channels][N = Cout] += A^T · G with the voxel rows as the contraction dimension, so
+// both operands are MN-major: the very same gathered [rows][64 ch] swizzled tiles the forward kernel builds serve as
+// A (LBO = distance between two 64-channel sub-tiles) and the gout tile as B (LBO = distance between 64-col blocks).
+// "sub-tile" s = (offset k, 64-channel block cb); a unit = two consecutive sub-tiles = one M=128 accumulator of
+// Cout TMEM columns; a CTA keeps 512/Cout units resident in TMEM, walks its share of 64-row tiles, and finally
+// adds its partial dW with fp32 reductions (red.global.add).
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace pasco;
+using namespace umma;
+
+namespace {
+
+constexpr int NUM_GATHER_WARPS = 4;
+constexpr int NUM_THREADS = 9 * 32;
+constexpr int MAX_STAGES = 8;
+constexpr int WG_R = 64;                  // voxel rows per tile (contraction block)
+constexpr int WG_SUB_BYTES = WG_R * 128;  // one [64 rows][64 ch] bf16 tile = 8 KB
+
+struct WgradParams {
+  const float* in;
+  const int32_t* nbr;
+  const float* gout;
+  const float* in_scale;
+  const float* in_shift;
+  float* dW;
+  int64_t n_out;
+  int K, Cin, Cout, in_act;
+  int stages, tmem_cols;
+  int units_per_pass, num_units, num_subs, passes, ctas_per_pass;
+};
+
+__device__ __forceinline__ float act_apply(float z, int act) {
+  if (act == 1) return fmaxf(z, 0.f);
+  if (act == 2) return z > 0.f ? z : 0.01f * z;
+  return z;
+}
+
+// gather one [WG_R rows][64 ch] tile: lane l<16 (and l+16) of each warp holds the source row of tile row w*16+l
+template <int NSPLIT, bool AFFINE_OK>
+__device__ __forceinline__ void gather_sub(uint8_t* dst_hi, uint8_t* dst_lo, const float* __restrict__ src, int ld,
+                                           int cbase_blk, int idx, int warp, int lane, const float* scale,
+                                           const float* shift, int act) {
+  const int chunk = lane & 15, rsub = lane >> 4;
+  const int cbase = cbase_blk + chunk * 4;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool affine = AFFINE_OK && scale != nullptr;
+  if (affine) {
+    sc = __ldg(reinterpret_cast<const float4*>(scale + cbase));
+    sh = __ldg(reinterpret_cast<const float4*>(shift + cbase));
+  }
+  float4 v[8];
+  int srcs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r = i * 2 + rsub;  // row within this warp's 16 rows
+    srcs[i] = __shfl_sync(0xffffffffu, idx, r);
+    v[i] = srcs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)srcs[i] * ld + cbase))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 x = v[i];
+    if (AFFINE_OK && (affine || act) && srcs[i] >= 0) {
+      x.x = act_apply(fmaf(x.x, sc.x, sh.x), act);
+      x.y = act_apply(fmaf(x.y, sc.y, sh.y), act);
+      x.z = act_apply(fmaf(x.z, sc.z, sh.z), act);
+      x.w = act_apply(fmaf(x.w, sc.w, sh.w), act);
+    }
+    const int trow = warp * 16 + i * 2 + rsub;
+    const uint32_t off = (uint32_t)trow * 128u + (uint32_t)(((chunk >> 1) ^ (trow & 7)) << 4) + (uint32_t)((chunk & 1) << 3);
+    uint2 hi, lo;
+    split4(x, hi, lo);
+    *reinterpret_cast<uint2*>(dst_hi + off) = hi;
+    if (NSPLIT == 3) *reinterpret_cast<uint2*>(dst_lo + off) = lo;
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int n_op = (NSPLIT == 3) ? 2 : 1;
+  const int NB = p.Cout / 64;                    // 64-column blocks of gout
+  const int g_bytes = n_op * NB * WG_SUB_BYTES;  // one gout tile (hi [+ lo])
+  const int a_bytes = n_op * 2 * WG_SUB_BYTES;   // one stage: two sub-tiles (hi [+ lo])
+  uint8_t* g_smem = smem;                        // [2][g_bytes]
+  uint8_t* a_smem = smem + 2 * (size_t)g_bytes;  // [stages][a_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)p.stages * a_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* gfull_bar = bars + 2 * MAX_STAGES;       // [2]
+  uint64_t* gempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
+  uint64_t* done_bar = bars + 2 * MAX_STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int CB = p.Cin / 64;
+  const int pass = blockIdx.x % p.passes;
+  const int cta_in_pass = blockIdx.x / p.passes;
+  const int unit0 = pass * p.units_per_pass;
+  const int nunits = min(p.units_per_pass, p.num_units - unit0);
+  const int64_t num_rt = (p.n_out + WG_R - 1) / WG_R;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(full_bar + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(gfull_bar + b), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(gempty_bar + b), 1);
+    }
+    mbar_init(smem_u32(done_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NUM_GATHER_WARPS) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int git = 0;
+    for (int64_t rt = cta_in_pass; rt < num_rt; rt += p.ctas_per_pass, ++git) {
+      const int gb = git & 1;
+      const int64_t my_row = rt * WG_R + warp * 16 + (lane & 15);
+      const bool row_ok = my_row < p.n_out;
+      // ---- gout tile (identity rows) ----
+      mbar_wait(smem_u32(gempty_bar + gb), ((git >> 1) & 1) ^ 1);
+      {
+        uint8_t* g = g_smem + (size_t)gb * g_bytes;
+        const int gidx = row_ok ? (int)my_row : -1;
+        for (int nb = 0; nb < NB; ++nb)
+          gather_sub<NSPLIT, false>(g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, p.gout, p.Cout,
+                                    nb * 64, gidx, warp, lane, nullptr, nullptr, 0);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(gfull_bar + gb));
+      }
+      // ---- gathered input sub-tiles, two per stage ----
+      for (int u = 0; u < nunits; ++u) {
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+        uint8_t* a = a_smem + (size_t)stage * a_bytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int sub = (unit0 + u) * 2 + h;
+          int idx = -1;
+          int cb = 0;
+          if (sub < p.num_subs) {
+            const int k = sub / CB;
+            cb = sub - k * CB;
+            if (row_ok) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + my_row) : (int)my_row;
+          }
+          gather_sub<NSPLIT, true>(a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, p.in, p.Cin, cb * 64,
+                                   idx, warp, lane, p.in_scale, p.in_shift, p.in_act);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int git = 0;
+      for (int64_t rt = cta_in_pass; rt < num_rt; rt += p.ctas_per_pass, ++git) {
+        const int gb = git & 1;
+        mbar_wait(smem_u32(gfull_bar + gb), (git >> 1) & 1);
+        tc_fence_after();
+        const uint32_t g_hi = smem_u32(g_smem + (size_t)gb * g_bytes);
+        const uint32_t g_lo = g_hi + NB * WG_SUB_BYTES;
+        for (int u = 0; u < nunits; ++u) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(a_smem + (size_t)stage * a_bytes);
+          const uint32_t a_lo = a_hi + 2 * WG_SUB_BYTES;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.Cout);
+#pragma unroll
+          for (int j = 0; j < WG_R / 16; ++j) {
+            const uint32_t acc = (git > 0 || j > 0) ? 1u : 0u;
+            const uint64_t da_hi = make_desc_sw128(a_hi + j * 2048, WG_SUB_BYTES, 1024);
+            const uint64_t db_hi = make_desc_sw128(g_hi + j * 2048, WG_SUB_BYTES, 1024);
+            mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
+            if (NSPLIT == 3) {
+              const uint64_t da_lo = make_desc_sw128(a_lo + j * 2048, WG_SUB_BYTES, 1024);
+              const uint64_t db_lo = make_desc_sw128(g_lo + j * 2048, WG_SUB_BYTES, 1024);
+              mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
+              mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+            }
+          }
+          mma_commit(smem_u32(empty_bar + stage));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(smem_u32(gempty_bar + gb));
+      }
+      mma_commit(smem_u32(done_bar));
+    }
+  } else {
+    // epilogue: after the CTA's last MMA, add the partial dW
+    const int q = warp - NUM_GATHER_WARPS;
+    const bool any_work = cta_in_pass < num_rt;
+    if (any_work) {
+      mbar_wait(smem_u32(done_bar), 0);
+      tc_fence_after();
+      const int L = q * 32 + lane;  // accumulator row = channel within the unit
+      for (int u = 0; u < nunits; ++u) {
+        const int sub = (unit0 + u) * 2 + (L >> 6);
+        const bool ok = sub < p.num_subs;
+        const int k = ok ? sub / CB : 0;
+        const int cb = ok ? sub - k * CB : 0;
+        float* drow = p.dW + ((int64_t)k * p.Cin + cb * 64 + (L & 63)) * p.Cout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * p.Cout);
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int pow2_cols(int c) {
+  int v = 32;
+  while (v < c) v <<= 1;
+  return v;
+}
+
+}  // namespace
+
+extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
+                                   int32_t Cin, int32_t Cout, const float* gout, const float* in_scale,
+                                   const float* in_shift, int32_t in_act, float* dW, int32_t precision,
+                                   pasco_stream_t s) {
+  PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_wgrad_tc: precision must be 1 or 3");
+  PASCO_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256,
+                  "pasco_conv_wgrad_tc: Cin (%d) and Cout (%d) must be multiples of 64, Cout <= 256", Cin, Cout);
+  (void)n_in;
+  if (n_out == 0) return 0;
+  int dev = 0, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int n_op = precision == 3 ? 2 : 1;
+  const int g_bytes = n_op * (Cout / 64) * WG_SUB_BYTES;
+  const int a_bytes = n_op * 2 * WG_SUB_BYTES;
+  const int fixed = 1024 + (2 * MAX_STAGES + 6) * 8 + 16;
+  int stages = (smem_optin - fixed - 2 * g_bytes) / a_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  PASCO_CHECK_ARG(stages >= 2, "pasco_conv_wgrad_tc: not enough shared memory");
+  WgradParams p;
+  p.in = in; p.nbr = nbr; p.gout = gout; p.in_scale = in_scale; p.in_shift = in_shift; p.dW = dW;
+  p.n_out = n_out; p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
+  p.stages = stages;
+  p.num_subs = K * (Cin / 64);
+  p.num_units = (p.num_subs + 1) / 2;
+  p.units_per_pass = 512 / Cout;
+  if (p.units_per_pass > p.num_units) p.units_per_pass = p.num_units;
+  p.tmem_cols = pow2_cols(p.units_per_pass * Cout);
+  p.passes = (p.num_units + p.units_per_pass - 1) / p.units_per_pass;
+  int64_t num_rt = (n_out + WG_R - 1) / WG_R;
+  int cpp = num_sms() / p.passes;
+  if (cpp < 1) cpp = 1;
+  if (cpp > num_rt) cpp = (int)num_rt;
+  p.ctas_per_pass = cpp;
+  const size_t smem = (size_t)2 * g_bytes + (size_t)stages * a_bytes + fixed;
+  const int grid = p.passes * cpp;
+  cudaError_t e;
+  if (precision == 3) {
+    e = cudaFuncSetAttribute(k_wgrad_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_wgrad_tc<3><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_wgrad_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_wgrad_tc<1><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("pasco_conv_wgrad_tc: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
+    return -1;
+  }
+  PASCO_CHECK_LAUNCH("pasco_conv_wgrad_tc");
+  return 0;
+}

@@ -1,0 +1,477 @@
+"""Tensor-level wrappers and autograd Functions over the C-ABI (include/pasco_sm100.h).
+
+Everything here runs on CUDA through libpasco_sm100.so; torch supplies device memory, the
+current stream and the autograd graph.  Row indices are int32, −1 = no row.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, int_array
+
+_PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
+_FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
+
+
+def set_precision(mode) -> None:
+    """'fp32' (bf16x3 split operands, ~2^-16 relative) or 'bf16' (single bf16 MMA)."""
+    global _PRECISION
+    _PRECISION = {"fp32": 3, "bf16": 1, 3: 3, 1: 1}[mode]
+
+
+def get_precision() -> int:
+    return _PRECISION
+
+
+def force_simt(flag: bool) -> None:
+    global _FORCE_SIMT
+    _FORCE_SIMT = bool(flag)
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.int32 else t.to(torch.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# hash tables / coordinate maps
+# ----------------------------------------------------------------------------------------------
+class HashTable:
+    """Open-addressing table key(b,x,y,z) → row, resident in HBM."""
+
+    def __init__(self, keys: torch.Tensor, vals: torch.Tensor):
+        self.keys, self.vals = keys, vals
+        self.capacity = keys.numel()
+
+
+def _capacity(n: int) -> int:
+    cap = 64
+    while cap < 2 * n:
+        cap <<= 1
+    return cap
+
+
+def hash_insert(coords: torch.Tensor) -> Tuple[HashTable, torch.Tensor]:
+    """Insert int32 [N,4] rows.  Returns (table, first_row[N]) — first_row[i] == i iff row i wins."""
+    n = coords.shape[0]
+    cap = _capacity(n)
+    dev = coords.device
+    keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)                 # 0xFF… = empty
+    vals = torch.full((cap,), 0x7F7F7F7F, dtype=torch.int32, device=dev)
+    first = torch.empty(n, dtype=torch.int32, device=dev)
+    call("pasco_hash_insert", ptr(coords), n, ptr(keys), ptr(vals), cap, ptr(first))
+    return HashTable(keys, vals), first
+
+
+def hash_lookup(table: HashTable, query: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(query.shape[0], dtype=torch.int32, device=query.device)
+    call("pasco_hash_lookup", ptr(query), query.shape[0], ptr(table.keys), ptr(table.vals), table.capacity, ptr(out))
+    return out
+
+
+def hash_remap(table: HashTable, new_row: torch.Tensor) -> None:
+    call("pasco_hash_remap", ptr(table.vals), table.capacity, ptr(new_row))
+
+
+def coords_floor(coords: torch.Tensor, stride: Sequence[int]) -> torch.Tensor:
+    out = torch.empty_like(coords)
+    call("pasco_coords_floor", ptr(coords), coords.shape[0], int(stride[0]), int(stride[1]), int(stride[2]), ptr(out))
+    return out
+
+
+def coords_generate_k2(coords: torch.Tensor, out_stride: Sequence[int]) -> torch.Tensor:
+    out = torch.empty(coords.shape[0] * 8, 4, dtype=torch.int32, device=coords.device)
+    call("pasco_coords_generate_k2", ptr(coords), coords.shape[0], int(out_stride[0]), int(out_stride[1]),
+         int(out_stride[2]), ptr(out))
+    return out
+
+
+def kernel_map_probe(out_coords: torch.Tensor, table: HashTable, kernel_size: int, step: Sequence[int]) -> torch.Tensor:
+    """nbr[K, N_out] for an odd kernel; step = tensor_stride·dilation per axis."""
+    n = out_coords.shape[0]
+    nbr = torch.empty(kernel_size ** 3, n, dtype=torch.int32, device=out_coords.device)
+    call("pasco_kernel_map_probe", ptr(out_coords), n, ptr(table.keys), ptr(table.vals), table.capacity,
+         kernel_size, int(step[0]), int(step[1]), int(step[2]), ptr(nbr))
+    return nbr
+
+
+def kernel_map_down(child_coords: torch.Tensor, parent_table: HashTable, n_parent: int, ks: int,
+                    child_stride: Sequence[int], want_nbr: bool = True):
+    n = child_coords.shape[0]
+    dev = child_coords.device
+    parent_of = torch.empty(n, dtype=torch.int32, device=dev)
+    slot_of = torch.empty(n, dtype=torch.int32, device=dev)
+    nbr = torch.full((ks ** 3, n_parent), -1, dtype=torch.int32, device=dev) if want_nbr else None
+    call("pasco_kernel_map_down", ptr(child_coords), n, ptr(parent_table.keys), ptr(parent_table.vals),
+         parent_table.capacity, ks, int(child_stride[0]), int(child_stride[1]), int(child_stride[2]),
+         ptr(parent_of), ptr(slot_of), ptr(nbr), n_parent)
+    return parent_of, slot_of, nbr
+
+
+# ----------------------------------------------------------------------------------------------
+# order-preserving compaction
+# ----------------------------------------------------------------------------------------------
+def compact(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """mask bool/uint8 [N] → (kept_rows[int32 N'], new_row[int32 N], N').  One host sync (N')."""
+    n = mask.shape[0]
+    dev = mask.device
+    m8 = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+    m8 = m8.contiguous()
+    if n == 0:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, z, 0
+    nb = (n + 1023) // 1024
+    counts = torch.empty(nb, dtype=torch.int32, device=dev)
+    call("pasco_mask_block_counts", ptr(m8), n, ptr(counts))
+    incl = torch.cumsum(counts, 0, dtype=torch.int32)       # ≤ ~1k elements: plumbing
+    offsets = (incl - counts).contiguous()
+    total = int(incl[-1].item())
+    new_row = torch.empty(n, dtype=torch.int32, device=dev)
+    kept = torch.empty(total, dtype=torch.int32, device=dev)
+    call("pasco_mask_compact", ptr(m8), n, ptr(offsets), ptr(new_row), ptr(kept))
+    return kept, new_row, total
+
+
+def gather_coords(coords: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(rows.shape[0], 4, dtype=torch.int32, device=coords.device)
+    call("pasco_gather_coords", ptr(coords), ptr(rows), rows.shape[0], ptr(out))
+    return out
+
+
+def _gather_rows(src: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(rows.shape[0], src.shape[1], dtype=torch.float32, device=src.device)
+    call("pasco_gather_rows", ptr(src), ptr(rows), rows.shape[0], src.shape[1], ptr(out))
+    return out
+
+
+def _scatter_rows(src: torch.Tensor, rows: torch.Tensor, dst: torch.Tensor, accumulate: bool) -> None:
+    call("pasco_scatter_rows", ptr(src), ptr(rows), rows.shape[0], src.shape[1], ptr(dst), int(accumulate))
+
+
+class GatherRows(torch.autograd.Function):
+    """out[r] = src[rows[r]] (rows unique or −1).  Backward scatters into a zero tensor."""
+
+    @staticmethod
+    def forward(ctx, src, rows):
+        ctx.save_for_backward(rows)
+        ctx.n_src = src.shape[0]
+        return _gather_rows(src.contiguous().float(), rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        (rows,) = ctx.saved_tensors
+        gin = torch.zeros(ctx.n_src, g.shape[1], dtype=torch.float32, device=g.device)
+        _scatter_rows(g.contiguous(), rows, gin, False)
+        return gin, None
+
+
+class UnionAdd(torch.autograd.Function):
+    """out = zeros[N_out]; out[:N_a] = a; out[rows_b] += b   (coordinate-union add, decoder_v3.py:163)."""
+
+    @staticmethod
+    def forward(ctx, a, b, rows_b, n_out):
+        ctx.save_for_backward(rows_b)
+        ctx.na = a.shape[0]
+        out = torch.zeros(n_out, a.shape[1], dtype=torch.float32, device=a.device)
+        out[: a.shape[0]].copy_(a)
+        _scatter_rows(b.contiguous(), rows_b, out, True)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rows_b,) = ctx.saved_tensors
+        g = g.contiguous()
+        return g[: ctx.na], _gather_rows(g, rows_b), None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# dense <-> sparse
+# ----------------------------------------------------------------------------------------------
+def _geom(min_c, stride):
+    return int_array(min_c), int_array(stride)
+
+
+class ToDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, coords, min_c, stride, shape):
+        B, Cc, X, Y, Z = shape
+        dense = torch.zeros(shape, dtype=torch.float32, device=feats.device)
+        mc, st = _geom(min_c, stride)
+        call("pasco_to_dense", ptr(feats.contiguous()), ptr(coords), feats.shape[0], Cc, mc, st, ptr(dense), B, X, Y, Z)
+        ctx.save_for_backward(coords)
+        ctx.meta = (tuple(min_c), tuple(stride), tuple(shape))
+        return dense
+
+    @staticmethod
+    def backward(ctx, g):
+        (coords,) = ctx.saved_tensors
+        min_c, stride, shape = ctx.meta
+        return from_dense_raw(g.contiguous(), coords, min_c, stride), None, None, None, None
+
+
+def from_dense_raw(dense: torch.Tensor, coords: torch.Tensor, min_c, stride) -> torch.Tensor:
+    B, Cc, X, Y, Z = dense.shape
+    feats = torch.empty(coords.shape[0], Cc, dtype=torch.float32, device=dense.device)
+    mc, st = _geom(min_c, stride)
+    call("pasco_from_dense", ptr(dense), ptr(coords), coords.shape[0], Cc, mc, st, ptr(feats), B, X, Y, Z)
+    return feats
+
+
+class FromDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dense, coords, min_c, stride):
+        ctx.save_for_backward(coords)
+        ctx.meta = (tuple(min_c), tuple(stride), tuple(dense.shape))
+        return from_dense_raw(dense.contiguous().float(), coords, min_c, stride)
+
+    @staticmethod
+    def backward(ctx, g):
+        (coords,) = ctx.saved_tensors
+        min_c, stride, shape = ctx.meta
+        B, Cc, X, Y, Z = shape
+        dense = torch.zeros(shape, dtype=torch.float32, device=g.device)
+        mc, st = _geom(min_c, stride)
+        call("pasco_to_dense", ptr(g.contiguous()), ptr(coords), g.shape[0], Cc, mc, st, ptr(dense), B, X, Y, Z)
+        return dense, None, None, None
+
+
+def dense_occupancy(dense: torch.Tensor) -> torch.Tensor:
+    B, Cc = dense.shape[:2]
+    cells = dense[0, 0].numel()
+    mask = torch.empty(B * cells, dtype=torch.uint8, device=dense.device)
+    call("pasco_dense_occupancy", ptr(dense), B, Cc, cells, ptr(mask))
+    return mask
+
+
+# ----------------------------------------------------------------------------------------------
+# sparse convolution
+# ----------------------------------------------------------------------------------------------
+class KernelMap:
+    """Neighbour tables of one (in_map, out_map, kernel) triple, both directions.
+
+    nbr   int32 [K, N_out]: input row feeding output row o through offset k (forward / wgrad)
+    nbr_t int32 [K, N_in] : output row fed by input row i, table row k' using weight slice koff_t[k']
+    """
+
+    def __init__(self, nbr, n_in, n_out, nbr_t=None, koff_t=None, build_t=None):
+        self.nbr, self.n_in, self.n_out = nbr, n_in, n_out
+        self._nbr_t, self._koff_t, self._build_t = nbr_t, koff_t, build_t
+        self.K = nbr.shape[0]
+
+    def transposed(self):
+        if self._nbr_t is None:
+            self._nbr_t, self._koff_t = self._build_t()
+        return self._nbr_t, self._koff_t
+
+
+_PACK_CACHE = {}
+
+
+def _packed(weight: torch.Tensor, transpose: bool) -> torch.Tensor:
+    """UMMA shared-memory image of W (re-packed when the parameter changes)."""
+    key = (weight.data_ptr(), transpose)
+    ver = weight._version
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2] == tuple(weight.shape):
+        return hit[1]
+    K, Cin, Cout = weight.shape
+    nbytes = _lib.load().pasco_conv_packed_bytes(K, Cin, Cout)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    call("pasco_conv_pack_weights", ptr(weight.detach().contiguous()), K, Cin, Cout, int(transpose), ptr(buf))
+    if len(_PACK_CACHE) > 4096:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (ver, buf, tuple(weight.shape))
+    return buf
+
+
+def _tc_ok(c_contract: int, c_out: int, K: int) -> bool:
+    return (not _FORCE_SIMT) and c_contract % 64 == 0 and c_out % 16 == 0 and 16 <= c_out <= 256 and K <= 32
+
+
+def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
+               transpose_w: bool, koff: Optional[Sequence[int]], bias: Optional[torch.Tensor] = None,
+               in_scale=None, in_shift=None, in_act: int = 0) -> torch.Tensor:
+    """out[o] = Σ_k act(feats·scale+shift)[nbr[k,o]] @ Wk, Wk = W[koff[k]] (transposed when transpose_w)."""
+    K, Cin, Cout = weight.shape
+    c_contract, c_out = (Cout, Cin) if transpose_w else (Cin, Cout)
+    assert feats.shape[1] == c_contract
+    feats = feats.contiguous()
+    out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
+    kk = nbr.shape[0] if nbr is not None else 1
+    koff_arr = int_array(koff) if koff is not None else None
+    if _tc_ok(c_contract, c_out, kk):
+        call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
+             ptr(_packed(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
+             ptr(out), _PRECISION)
+    else:
+        assert in_scale is None and in_act == 0, "fused prologue needs the tensor-core path"
+        if nbr is None:
+            nbr = torch.arange(n_out, dtype=torch.int32, device=feats.device).view(1, -1)
+        call("pasco_conv_forward_simt", ptr(feats), ptr(nbr), kk, n_out, c_contract, c_out,
+             ptr(weight.detach().contiguous()), int(transpose_w), koff_arr, ptr(bias), ptr(out))
+    return out
+
+
+def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor], K: int, Cin: int, Cout: int,
+               in_scale=None, in_shift=None, in_act: int = 0) -> torch.Tensor:
+    n_out = gout.shape[0]
+    dW = torch.zeros(K, Cin, Cout, dtype=torch.float32, device=feats.device)
+    feats, gout = feats.contiguous(), gout.contiguous()
+    if (not _FORCE_SIMT) and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256:
+        call("pasco_conv_wgrad_tc", ptr(feats), feats.shape[0], ptr(nbr), K, n_out, Cin, Cout, ptr(gout),
+             ptr(in_scale), ptr(in_shift), in_act, ptr(dW), _PRECISION)
+    else:
+        assert in_scale is None and in_act == 0
+        if nbr is None:
+            nbr = torch.arange(n_out, dtype=torch.int32, device=feats.device).view(1, -1)
+        call("pasco_conv_wgrad_simt", ptr(feats), ptr(nbr), K, n_out, Cin, Cout, ptr(gout), ptr(dW))
+    return dW
+
+
+class SparseConv(torch.autograd.Function):
+    """ME ConvolutionForward/Backward over a cached KernelMap."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, kmap: KernelMap):
+        ctx.kmap = kmap
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(feats, weight)
+        return conv_apply(feats, weight, kmap.nbr, kmap.n_out, False, None,
+                          bias.view(-1).contiguous() if bias is not None else None)
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, weight = ctx.saved_tensors
+        kmap: KernelMap = ctx.kmap
+        g = g.contiguous()
+        gin = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            nbr_t, koff_t = kmap.transposed()
+            gin = conv_apply(g, weight, nbr_t, kmap.n_in, True, koff_t)
+        if ctx.needs_input_grad[1]:
+            K, Cin, Cout = weight.shape
+            gw = conv_wgrad(feats, g, kmap.nbr, K, Cin, Cout)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0, keepdim=True)
+        return gin, gw, gb, None
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling / reductions
+# ----------------------------------------------------------------------------------------------
+class MaxPoolRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, parent_of, n_parent):
+        feats = feats.contiguous()
+        out = torch.full((n_parent, feats.shape[1]), float("-inf"), dtype=torch.float32, device=feats.device)
+        call("pasco_maxpool_forward", ptr(feats), ptr(parent_of), feats.shape[0], feats.shape[1], ptr(out))
+        ctx.save_for_backward(feats, parent_of, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, parent_of, out = ctx.saved_tensors
+        p = parent_of.long()
+        hit = feats == out[p]
+        return torch.where(hit, g[p], torch.zeros_like(feats)), None, None
+
+
+class ScatterMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, index, n_seg):
+        src = src.contiguous().float()
+        index = index.contiguous().long()
+        out = torch.full((n_seg, src.shape[1]), float("-inf"), dtype=torch.float32, device=src.device)
+        arg = torch.full((n_seg, src.shape[1]), src.shape[0], dtype=torch.int64, device=src.device)
+        call("pasco_scatter_max", ptr(src), ptr(index), src.shape[0], src.shape[1], ptr(out), n_seg, ptr(arg))
+        ctx.save_for_backward(arg)
+        ctx.n_src = src.shape[0]
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (arg,) = ctx.saved_tensors
+        gsrc = torch.zeros(ctx.n_src + 1, g.shape[1], dtype=g.dtype, device=g.device)
+        gsrc.scatter_(0, arg, g)            # arg == n_src for empty segments → dummy row
+        return gsrc[: ctx.n_src], None, None
+
+
+def scatter_max(src: torch.Tensor, index: torch.Tensor, dim: int = 0, out=None, dim_size: Optional[int] = None):
+    """torch_scatter.scatter_max(src[P,C], index[P], dim=0) → (values, argmax); empty segments → 0
+    (pasco/models/unet3d_sparse_v2.py:79)."""
+    if dim != 0 or src.ndim != 2 or out is not None:
+        raise NotImplementedError("pasco_b200.scatter_max: only src[P,C], dim=0 is on PaSCo's path")
+    n_seg = int(index.max().item()) + 1 if dim_size is None else int(dim_size)
+    return ScatterMax.apply(src, index, n_seg)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused BatchNorm (+ activation) over rows
+# ----------------------------------------------------------------------------------------------
+def column_stats(x: torch.Tensor) -> torch.Tensor:
+    """float64 [2, C]: column sums and sums of squares."""
+    stats = torch.zeros(2, x.shape[1], dtype=torch.float64, device=x.device)
+    call("pasco_bn_stats", ptr(x), x.shape[0], x.shape[1], ptr(stats))
+    return stats
+
+
+def affine_act(x, scale, shift, act: int = 0, residual=None):
+    y = torch.empty_like(x)
+    call("pasco_affine_act", ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), act, ptr(residual), ptr(y))
+    return y
+
+
+class BatchNormAct(torch.autograd.Function):
+    """y = act(BN(x)) with training-mode batch statistics over all rows (optionally summed over
+    ranks = SyncBatchNorm); one stats pass + one apply pass; backward one reduce + one apply."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, act, group):
+        x = x.contiguous()
+        n = x.shape[0]
+        stats = column_stats(x)
+        count = torch.tensor([float(n)], dtype=torch.float64, device=x.device)
+        if group is not None:
+            packed = torch.cat([stats.view(-1), count])
+            torch.distributed.all_reduce(packed, group=group)
+            stats, count = packed[:-1].view(2, -1), packed[-1:]
+        mean = stats[0] / count
+        var = (stats[1] / count - mean * mean).clamp_(min=0)
+        rstd = torch.rsqrt(var + eps)
+        scale = (gamma.double() * rstd).float()
+        shift = (beta.double() - mean * gamma.double() * rstd).float()
+        y = affine_act(x, scale, shift, act)
+        ctx.save_for_backward(x, gamma, scale, shift, mean.float(), rstd.float(), count)
+        ctx.act, ctx.group = act, group
+        ctx.mark_non_differentiable(mean, var, count)
+        return y, mean, var, count
+
+    @staticmethod
+    def backward(ctx, gy, *_):
+        x, gamma, scale, shift, mean, rstd, count = ctx.saved_tensors
+        gy = gy.contiguous()
+        sums = torch.zeros(2, x.shape[1], dtype=torch.float64, device=x.device)
+        call("pasco_bn_bwd_reduce", ptr(gy), ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ctx.act, ptr(sums))
+        if ctx.group is not None:
+            torch.distributed.all_reduce(sums, group=ctx.group)
+        s_dz, s_dzx = sums[0], sums[1]
+        md, rd, gd = mean.double(), rstd.double(), gamma.double()
+        s_dzxhat = rd * (s_dzx - md * s_dz)
+        # NOTE: with a process group the reference (SyncBatchNorm) returns the *local* dgamma/dbeta
+        # contributions reduced by DDP; sums here are global, so divide back by world size in that case.
+        ggamma, gbeta = s_dzxhat, s_dz
+        if ctx.group is not None:
+            ws = torch.distributed.get_world_size(ctx.group)
+            ggamma, gbeta = ggamma / ws, gbeta / ws
+        m1, m2 = s_dz / count, s_dzxhat / count
+        ca = (gd * rd).float()
+        cb = (-gd * rd * rd * m2).float()
+        cc = (gd * rd * (md * rd * m2 - m1)).float()
+        gx = torch.empty_like(x)
+        call("pasco_bn_bwd_apply", ptr(gy), ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ctx.act,
+             ptr(ca), ptr(cb), ptr(cc), ptr(gx))
+        return gx, ggamma.float(), gbeta.float(), None, None, None

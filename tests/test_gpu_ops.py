@@ -1,0 +1,364 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Integer work (coordinate maps, kernel maps) must match bit-exactly after canonicalisation
+(rows sorted by (b,x,y,z); kernel maps compared as sets of (k, in_coord, out_coord) triples —
+SURVEY.md §8c item 3).  fp32 features: max-abs-normalised error ≤ 1e-3 (north_star), in practice
+~1e-5 for the bf16x3 path and exactly-rounded fp32 for the CUDA-core path.
+"""
+import pytest
+import torch
+
+import me_oracle as OR
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-3      # north_star tolerance for fp32 features
+TOL_TIGHT = 2e-5     # what bf16x3 / fp32 SIMT actually deliver
+TOL_BF16 = 2e-2      # bf16 operands
+
+
+@pytest.fixture(scope="module")
+def ME():
+    from pasco_b200 import build
+    build.build()
+    from pasco_b200 import me
+    return me
+
+
+def scene(shape=(24, 20, 12), p=0.3, C=64, batch=1, lo=(0, 0, 0), seed=0, stride=1):
+    g = torch.Generator().manual_seed(seed)
+    cs = []
+    for b in range(batch):
+        occ = torch.rand(*shape, generator=g) < p
+        c = torch.nonzero(occ).int() * stride + torch.tensor(lo, dtype=torch.int32)
+        cs.append(c)
+    bc = OR.utils.batched_coordinates(cs)
+    f = torch.randn(bc.shape[0], C, generator=g)
+    return bc, f
+
+
+def relerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def canon(C, F=None):
+    """Sort rows by packed coordinate key."""
+    C = C.detach().cpu()
+    order = torch.argsort(OR.pack_keys(C))
+    return (C[order], None if F is None else F.detach().cpu()[order])
+
+
+def assert_same_sparse(got, ref, tol):
+    gc, gf = canon(got.C, got.F)
+    rc, rf = canon(ref.C, ref.F)
+    assert gc.shape == rc.shape and torch.equal(gc, rc), "coordinate sets differ"
+    assert got.tensor_stride == ref.tensor_stride
+    e = relerr(gf, rf)
+    assert e <= tol, f"feature error {e:.3e} > {tol}"
+    return e
+
+
+def triples(nbr, in_c, out_c):
+    """Canonical set of (k, in_key, out_key) triples of a neighbour table."""
+    nbr = nbr.detach().cpu().long()
+    ik, ok = OR.pack_keys(in_c.detach().cpu()), OR.pack_keys(out_c.detach().cpu())
+    k, o = torch.nonzero(nbr >= 0, as_tuple=True)
+    t = torch.stack([k, ik[nbr[k, o]], ok[o]], 1)
+    return sorted(map(tuple, t.tolist()))
+
+
+# ------------------------------------------------------------------------------------------------
+# integer parity
+# ------------------------------------------------------------------------------------------------
+def test_insert_dedups_first_wins_and_keeps_order(ME):
+    C, F = scene(p=0.2, C=8, lo=(-8, 4, -2))
+    C2 = torch.cat([C, C[:50]], 0)
+    F2 = torch.cat([F, F[:50] + 100.0], 0)
+    ref = OR.SparseTensor(F2, C2)
+    got = ME.SparseTensor(F2.cuda(), C2.cuda())
+    assert torch.equal(got.C.cpu(), ref.C) and torch.equal(got.F.cpu(), ref.F)
+
+
+@pytest.mark.parametrize("lo", [(0, 0, 0), (-16, -8, -4)])
+def test_kernel_map_k3_bit_exact(ME, lo):
+    C, F = scene(C=8, batch=2, lo=lo)
+    ref = OR.SparseTensor(F, C)
+    got = ME.SparseTensor(F.cuda(), C.cuda())
+    rk = ref.coordinate_manager.kernel_map(ref.coordinate_map_key, ref.coordinate_map_key, 3)
+    gk = got.coordinate_manager.kernel_map(got.coordinate_map_key, got.coordinate_map_key, 3, 1, 1, False)
+    assert gk.nbr.shape == rk.shape
+    assert triples(gk.nbr, got.C, got.C) == triples(rk, ref.C, ref.C)
+    nbr_t, koff = gk.transposed()
+    assert koff == [26 - k for k in range(27)]
+
+
+@pytest.mark.parametrize("lo", [(0, 0, 0), (-16, -8, -4)])
+def test_stride_map_and_down_kernel_map_bit_exact(ME, lo):
+    C, F = scene(C=8, batch=2, lo=lo)
+    ref = OR.SparseTensor(F, C)
+    got = ME.SparseTensor(F.cuda(), C.cuda())
+    rcm, gcm = ref.coordinate_manager, got.coordinate_manager
+    rkey, gkey = rcm.stride(ref.coordinate_map_key, 2), gcm.stride(got.coordinate_map_key, 2)
+    assert torch.equal(canon(gcm.get_coordinates(gkey))[0], canon(rcm.get_coordinates(rkey))[0])
+    rk = rcm.kernel_map(ref.coordinate_map_key, rkey, 2)
+    gk = gcm.kernel_map(got.coordinate_map_key, gkey, 2, 2, 1, False)
+    assert triples(gk.nbr, got.C, gcm.get_coordinates(gkey)) == triples(rk, ref.C, rcm.get_coordinates(rkey))
+    nbr_t, _ = gk.transposed()          # table over children: exactly one parent each
+    assert int((nbr_t >= 0).sum()) == C.shape[0]
+
+
+def test_generative_map_union_and_prune_bit_exact(ME):
+    C, F = scene(shape=(6, 5, 4), p=0.5, C=8, stride=2, lo=(-4, 0, 2))
+    ref = OR.SparseTensor(F, C, tensor_stride=2)
+    got = ME.SparseTensor(F.cuda(), C.cuda(), tensor_stride=2)
+    rkey = ref.coordinate_manager.generate(ref.coordinate_map_key, 2, 2)
+    gkey = got.coordinate_manager.generate(got.coordinate_map_key, 2, 2)
+    rc, gc = ref.coordinate_manager.get_coordinates(rkey), got.coordinate_manager.get_coordinates(gkey)
+    assert torch.equal(canon(gc)[0], canon(rc)[0]) and gkey.tensor_stride == (1, 1, 1)
+    # union of two partially overlapping sets inside one manager
+    C2, F2 = scene(shape=(12, 10, 8), p=0.3, C=8, seed=5, lo=(-4, 0, 2))
+    ra = OR.SparseTensor(torch.ones(rc.shape[0], 8), coordinate_map_key=rkey, coordinate_manager=ref.coordinate_manager)
+    rb = OR.SparseTensor(F2, C2, coordinate_manager=ref.coordinate_manager)
+    ga = ME.SparseTensor(torch.ones(gc.shape[0], 8).cuda(), coordinate_map_key=gkey,
+                         coordinate_manager=got.coordinate_manager)
+    gb = ME.SparseTensor(F2.cuda(), C2.cuda(), coordinate_manager=got.coordinate_manager)
+    assert_same_sparse(ga + gb, ra + rb, 0.0)
+    # prune keeps order
+    m = torch.rand(C2.shape[0], generator=torch.Generator().manual_seed(3)) < 0.4
+    rp, gp = OR.MinkowskiPruning()(rb, m), ME.MinkowskiPruning()(gb, m.cuda())
+    assert torch.equal(gp.C.cpu(), rp.C) and torch.equal(gp.F.cpu(), rp.F)
+    assert ME.MinkowskiPruning()(gb, torch.zeros_like(m).cuda()).F.shape == (0, 8)
+    with pytest.raises(RuntimeError):
+        ME.MinkowskiPruning()(gb, m[:-1].cuda())
+
+
+def test_dense_and_to_sparse_match(ME):
+    C, F = scene(shape=(9, 7, 5), p=0.4, C=6, batch=2, lo=(-4, 0, 2))
+    F[5] = 0
+    ref, got = OR.SparseTensor(F, C), ME.SparseTensor(F.cuda(), C.cuda())
+    mn = torch.IntTensor([-4, 0, 2])
+    rd, gd = ref.dense(min_coordinate=mn)[0], got.dense(min_coordinate=mn)[0]
+    assert rd.shape == gd.shape and torch.equal(gd.cpu(), rd)
+    rs, gs = OR.to_sparse(rd), ME.to_sparse(gd)
+    assert torch.equal(gs.C.cpu(), rs.C) and torch.equal(gs.F.cpu(), rs.F)
+    with pytest.raises(ValueError):
+        got.dense()
+    shp = torch.Size([2, 6, 12, 8, 6])
+    assert torch.equal(got.dense(shp, min_coordinate=mn)[0].cpu(), ref.dense(shp, min_coordinate=mn)[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution parity (forward + both gradients), tensor-core and CUDA-core paths
+# ------------------------------------------------------------------------------------------------
+def _conv_pair(ME, kind, cin, cout, seed=0, bias=False):
+    torch.manual_seed(seed)
+    if kind == "k3":
+        r = OR.MinkowskiConvolution(cin, cout, kernel_size=3, bias=bias, dimension=3)
+        g = ME.MinkowskiConvolution(cin, cout, kernel_size=3, bias=bias, dimension=3)
+    elif kind == "down":
+        r = OR.MinkowskiConvolution(cin, cout, kernel_size=2, stride=2, dimension=3)
+        g = ME.MinkowskiConvolution(cin, cout, kernel_size=2, stride=2, dimension=3)
+    else:
+        r = OR.MinkowskiConvolutionTranspose(cin, cout, kernel_size=2, stride=2, dimension=3, expand_coordinates=True)
+        g = ME.MinkowskiConvolutionTranspose(cin, cout, kernel_size=2, stride=2, dimension=3, expand_coordinates=True)
+    g.load_state_dict(r.state_dict())
+    return r, g.cuda()
+
+
+def _run_conv_case(ME, kind, cin, cout, tol, shape=(20, 18, 10), p=0.3, bias=False):
+    ts = 2 if kind == "up" else 1
+    C, F = scene(shape=shape, p=p, C=cin, batch=2, lo=(-8, 0, 4), stride=ts)
+    rconv, gconv = _conv_pair(ME, kind, cin, cout, bias=bias)
+    Fr = F.clone().requires_grad_(True)
+    Fg = F.clone().cuda().requires_grad_(True)
+    ref = rconv(OR.SparseTensor(Fr, C, tensor_stride=ts))
+    got = gconv(ME.SparseTensor(Fg, C.cuda(), tensor_stride=ts))
+    e_f = assert_same_sparse(got, ref, tol)
+    # same upstream gradient on matching rows
+    order_r = torch.argsort(OR.pack_keys(ref.C))
+    order_g = torch.argsort(OR.pack_keys(got.C.cpu()))
+    gup = torch.randn(ref.F.shape, generator=torch.Generator().manual_seed(7))
+    gr = torch.empty_like(gup)
+    gr[order_r] = gup
+    gg = torch.empty_like(gup)
+    gg[order_g] = gup
+    ref.F.backward(gr)
+    got.F.backward(gg.cuda())
+    e_i = relerr(Fg.grad, Fr.grad)
+    e_w = relerr(gconv.kernel.grad, rconv.kernel.grad)
+    assert e_i <= tol, f"dgrad error {e_i:.3e}"
+    assert e_w <= tol, f"wgrad error {e_w:.3e}"
+    if bias:
+        assert relerr(gconv.bias.grad, rconv.bias.grad) <= tol
+    return e_f, e_i, e_w
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 128, 128), ("k3", 256, 256), ("down", 64, 128),
+                                           ("down", 128, 256), ("up", 256, 128), ("up", 128, 64), ("k3", 64, 128)])
+def test_conv_tensor_core_fp32_mode(ME, kind, cin, cout):
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    ops.force_simt(False)
+    e = _run_conv_case(ME, kind, cin, cout, TOL_TIGHT, bias=(kind == "k3" and cin == 64 and cout == 64))
+    print(f"bf16x3 {kind} {cin}->{cout}: fwd {e[0]:.2e} dgrad {e[1]:.2e} wgrad {e[2]:.2e}")
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("down", 64, 128), ("up", 128, 64)])
+def test_conv_tensor_core_bf16_mode(ME, kind, cin, cout):
+    from pasco_b200 import ops
+    ops.set_precision("bf16")
+    try:
+        e = _run_conv_case(ME, kind, cin, cout, TOL_BF16)
+        print(f"bf16 {kind} {cin}->{cout}: fwd {e[0]:.2e} dgrad {e[1]:.2e} wgrad {e[2]:.2e}")
+    finally:
+        ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 24, 40), ("down", 16, 24), ("up", 24, 8)])
+def test_conv_cuda_core_path(ME, kind, cin, cout):
+    from pasco_b200 import ops
+    ops.force_simt(True)
+    try:
+        e = _run_conv_case(ME, kind, cin, cout, TOL_TIGHT, shape=(12, 10, 8))
+    finally:
+        ops.force_simt(False)
+
+
+def test_conv_tile_tail_and_single_voxel(ME):
+    """n_out not a multiple of the 128-row tile, and a 1-voxel tensor."""
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    for shape, p in (((7, 6, 5), 0.63), ((1, 1, 1), 1.1)):
+        C, F = scene(shape=shape, p=p, C=64)
+        rconv, gconv = _conv_pair(ME, "k3", 64, 64)
+        assert_same_sparse(gconv(ME.SparseTensor(F.cuda(), C.cuda())), rconv(OR.SparseTensor(F, C)), TOL_TIGHT)
+
+
+def test_conv_full_grid_matches_dense_conv3d(ME):
+    """Independent of the oracle: on a fully occupied grid the sparse conv IS F.conv3d(padding=1)."""
+    import torch.nn.functional as Fn
+    X, Y, Z, Cc = 10, 9, 8, 64
+    g = torch.Generator().manual_seed(1)
+    dense = torch.randn(1, Cc, X, Y, Z, generator=g)
+    idx = torch.nonzero(torch.ones(X, Y, Z)).int()
+    C = OR.utils.batched_coordinates([idx])
+    F = dense[0, :, idx[:, 0].long(), idx[:, 1].long(), idx[:, 2].long()].t().contiguous()
+    conv = ME.MinkowskiConvolution(Cc, Cc, kernel_size=3, dimension=3).cuda()
+    y = conv(ME.SparseTensor(F.cuda(), C.cuda()))
+    w = conv.kernel.detach().cpu().view(3, 3, 3, Cc, Cc).permute(4, 3, 2, 1, 0).contiguous()
+    ref = Fn.conv3d(dense.double(), w.double(), padding=1)[0]
+    c = y.C.cpu().long()
+    assert relerr(y.F, ref[:, c[:, 1], c[:, 2], c[:, 3]].t()) <= TOL_TIGHT
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / scatter-max / batch-norm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s", [2, 4])
+def test_maxpool_matches(ME, s):
+    C, F = scene(shape=(16, 12, 8), p=0.4, C=10, batch=2, lo=(-8, 0, 4))
+    ref = OR.MinkowskiMaxPooling(kernel_size=s, stride=s, dimension=3)(OR.SparseTensor(F, C))
+    got = ME.MinkowskiMaxPooling(kernel_size=s, stride=s, dimension=3)(ME.SparseTensor(F.cuda(), C.cuda()))
+    assert_same_sparse(got, ref, 0.0)
+
+
+def test_scatter_max_matches(ME):
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(5000, 64, generator=g)
+    idx = torch.randint(0, 700, (5000,), generator=g)
+    idx[idx == 13] = 14                                       # an empty segment
+    rv, ra = OR.scatter_max(src, idx, dim=0)
+    src_g = src.clone().cuda().requires_grad_(True)
+    gv, ga = ME.scatter_max(src_g, idx.cuda(), dim=0)
+    assert torch.equal(gv.cpu(), rv) and torch.equal(ga.cpu(), ra)
+    assert float(gv[13].abs().sum()) == 0.0
+    src_r = src.clone().requires_grad_(True)
+    OR.scatter_max(src_r, idx, dim=0)[0].sum().backward()
+    gv.sum().backward()
+    assert torch.equal(src_g.grad.cpu(), src_r.grad)
+
+
+@pytest.mark.parametrize("C,act", [(64, 1), (67, 0), (128, 2), (20, 1)])
+def test_fused_batchnorm_act_forward_backward(ME, C, act):
+    from pasco_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(3001, C, generator=g) * 2 + 0.5)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    up = torch.randn(3001, C, generator=g)
+    xr = x.clone().double().requires_grad_(True)
+    gr, br = gamma.clone().double().requires_grad_(True), beta.clone().double().requires_grad_(True)
+    z = torch.nn.functional.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5)
+    yr = [z, torch.relu(z), torch.nn.functional.leaky_relu(z, 0.01)][act]
+    (yr * up.double()).sum().backward()
+    xg = x.clone().cuda().requires_grad_(True)
+    gg, bg = gamma.clone().cuda().requires_grad_(True), beta.clone().cuda().requires_grad_(True)
+    yg, mean, var, cnt = ops.BatchNormAct.apply(xg, gg, bg, 1e-5, act, None)
+    (yg * up.cuda()).sum().backward()
+    assert relerr(yg, yr) <= TOL_TIGHT
+    assert relerr(xg.grad, xr.grad) <= 1e-4 and relerr(gg.grad, gr.grad) <= 1e-4 and relerr(bg.grad, br.grad) <= 1e-4
+    assert relerr(mean, x.double().mean(0)) <= 1e-6 and relerr(var, x.double().var(0, unbiased=False)) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# a residual U-Net slice written against the ME API (what pasco/maskpls/mink.py composes)
+# ------------------------------------------------------------------------------------------------
+def _mini_net(M):
+    import torch.nn as nn
+
+    class Res(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.net = nn.Sequential(M.MinkowskiBatchNorm(c), M.MinkowskiReLU(inplace=True),
+                                     M.MinkowskiConvolution(c, c, kernel_size=3, dimension=3),
+                                     M.MinkowskiBatchNorm(c), M.MinkowskiReLU(inplace=True),
+                                     M.MinkowskiConvolution(c, c, kernel_size=3, dimension=3))
+            self.relu = M.MinkowskiReLU(inplace=True)
+
+        def forward(self, x):
+            return self.relu(x + self.net(x))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = M.MinkowskiConvolution(16, 64, kernel_size=1, dimension=3)
+            self.r1 = Res(64)
+            self.down = nn.Sequential(M.MinkowskiConvolution(64, 128, kernel_size=2, stride=2, dimension=3),
+                                      M.MinkowskiBatchNorm(128), M.MinkowskiLeakyReLU(inplace=True))
+            self.r2 = Res(128)
+            self.up = nn.Sequential(M.MinkowskiConvolutionTranspose(128, 64, kernel_size=2, stride=2, dimension=3,
+                                                                    expand_coordinates=True),
+                                    M.MinkowskiBatchNorm(64), M.MinkowskiLeakyReLU(inplace=True))
+            self.r3 = Res(64)
+            self.head = M.MinkowskiConvolution(64, 20, kernel_size=1, bias=True, dimension=3)
+            self.prune = M.MinkowskiPruning()
+
+        def forward(self, x):
+            s1 = self.r1(self.stem(x))
+            s2 = self.r2(self.down(s1))
+            u = self.up(s2)
+            keep = (u.C[:, 1] >= 0) & (u.C[:, 1] < 20) & (u.C[:, 2] >= 0) & (u.C[:, 3] >= 0)
+            u = self.prune(u, keep)
+            return self.head(self.r3(u + s1))
+    return Net()
+
+
+def test_unet_slice_forward_backward_matches_oracle(ME):
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    torch.manual_seed(0)
+    rnet = _mini_net(OR)
+    gnet = _mini_net(ME)
+    gnet.load_state_dict(rnet.state_dict())
+    gnet.cuda()
+    C, F = scene(shape=(20, 16, 8), p=0.25, C=16, batch=1)
+    ry = rnet(OR.SparseTensor(F, C))
+    gy = gnet(ME.SparseTensor(F.cuda(), C.cuda()))
+    e = assert_same_sparse(gy, ry, TOL_FP32)
+    (ry.F ** 2).mean().backward()
+    (gy.F ** 2).mean().backward()
+    worst = 0.0
+    for (n, pr), (_, pg) in zip(rnet.named_parameters(), gnet.named_parameters()):
+        worst = max(worst, relerr(pg.grad, pr.grad))
+        assert relerr(pg.grad, pr.grad) <= 5e-3, n
+    print(f"unet slice: fwd {e:.2e}, worst param-grad {worst:.2e}")
