@@ -1,0 +1,128 @@
+"""Training losses that close the fwd+bwd loop of the benchmark: a compact restatement (torch ops +
+SciPy Hungarian on the host) of what PaSCo trains with — SURVEY.md §8f "next #4" rows, not kernels.
+
+  completion_loss   pasco/loss/losses.py:124-179  (class-weighted CE + Lovász-softmax on the sparse
+                    semantic logits at scales 1, 2, 4; labels sampled at the voxel coordinates)
+  panoptic_set_loss pasco/loss/criterion_sparse.py:19-411 + matcher_sparse.py:69-157  (Hungarian matching of
+                    100 queries to the instance masks on cost = class prob + focal + dice; class CE with
+                    no-object weight, mask focal + dice on the matched pairs, also on the aux levels)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from scipy.optimize import linear_sum_assignment
+
+
+def lovasz_softmax_present(probs: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """Lovász-softmax over the classes present in `labels` (Berman et al. 2018)."""
+    losses = []
+    for c in torch.unique(labels).tolist():
+        fg = (labels == c).float()
+        err = (fg - probs[:, c]).abs()
+        err_sorted, perm = torch.sort(err, descending=True)
+        fg_sorted = fg[perm]
+        gts = fg_sorted.sum()
+        inter = gts - fg_sorted.cumsum(0)
+        union = gts + (1 - fg_sorted).cumsum(0)
+        jac = 1.0 - inter / union
+        jac = torch.cat([jac[:1], jac[1:] - jac[:-1]])
+        losses.append(torch.dot(err_sorted, jac))
+    return torch.stack(losses).mean() if losses else probs.sum() * 0
+
+
+def completion_loss(sem_logits_at_scales: Dict[int, list], sem_labels: Dict[str, torch.Tensor], min_Cs,
+                    class_frequencies) -> torch.Tensor:
+    ces, lovs = [], []
+    for scale, per_subnet in sem_logits_at_scales.items():
+        fr = np.asarray(class_frequencies[f"1_{scale}"], dtype=np.float64)
+        w = fr / fr.sum()
+        w = torch.from_numpy(np.power(np.amax(w) / w, 1 / 3.0)).float()
+        for m, lg in enumerate(per_subnet):
+            if lg.F.shape[0] == 0:
+                continue
+            c = (lg.C[:, 1:].long() - min_Cs[m].to(lg.C.device).view(1, 3)) // scale
+            tgt = sem_labels[f"1_{scale}"][m]
+            inside = ((c >= 0).all(1) & (c[:, 0] < tgt.shape[0]) & (c[:, 1] < tgt.shape[1]) & (c[:, 2] < tgt.shape[2]))
+            c, logits = c[inside], lg.F[inside]
+            t = tgt[c[:, 0], c[:, 1], c[:, 2]].long()
+            valid = t != 255
+            ces.append(F.cross_entropy(logits, t, weight=w.to(logits), ignore_index=255))
+            lovs.append(lovasz_softmax_present(F.softmax(logits[valid], 1), t[valid]))
+    if not ces:
+        return torch.zeros((), requires_grad=True)
+    return torch.stack(ces).mean() + torch.stack(lovs).mean()
+
+
+def _focal(logits, targets, alpha=0.25, gamma=2.0):
+    p = torch.sigmoid(logits)
+    ce = F.binary_cross_entropy_with_logits(logits, targets, reduction="none")
+    pt = p * targets + (1 - p) * (1 - targets)
+    return (alpha * targets + (1 - alpha) * (1 - targets)) * ce * (1 - pt) ** gamma
+
+
+@torch.no_grad()
+def hungarian(query_logits, mask_logits, tgt_cls, tgt_masks, w_class=1.0, w_mask=20.0, w_dice=1.0):
+    """query_logits [Q,K+1], mask_logits [P,Q], tgt_masks [T,P] → (query idx, target idx).  CPU crossing
+    exactly where the reference has one (matcher_sparse.py:151)."""
+    prob = query_logits.softmax(-1)
+    out = mask_logits.t()                                           # [Q,P]
+    cost_class = -prob[:, tgt_cls]
+    sig = out.sigmoid()
+    num = 2 * sig @ tgt_masks.t()
+    den = sig.sum(-1)[:, None] + tgt_masks.sum(-1)[None, :]
+    cost_dice = 1 - (num + 1) / (den + 1)
+    P = max(out.shape[1], 1)
+    pos = _focal(out, torch.ones_like(out))
+    neg = _focal(out, torch.zeros_like(out))
+    cost_mask = (pos @ tgt_masks.t() + neg @ (1 - tgt_masks).t()) / P
+    C = w_mask * cost_mask + w_class * cost_class + w_dice * cost_dice
+    i, j = linear_sum_assignment(C.float().cpu().numpy())
+    return torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)
+
+
+def panoptic_set_loss(pred: Dict, tgt_cls: torch.Tensor, tgt_masks: torch.Tensor, n_classes: int, eos_coef=0.1,
+                      w_ce=2.0, w_mask=20.0, w_dice=1.0) -> torch.Tensor:
+    """pred = one entry of panop_predictions; tgt_masks float [T,P] sampled at pred['voxel_logits'].C."""
+    levels = [(pred["query_logits"], pred["voxel_logits"].F)] + \
+             [(a["query_logits"], a["voxel_logits"].F) for a in pred.get("aux_outputs", [])]
+    dev = levels[0][0].device
+    qi, tj = hungarian(levels[0][0][0], levels[0][1], tgt_cls, tgt_masks)
+    qi, tj = qi.to(dev), tj.to(dev)
+    empty_w = torch.ones(n_classes + 1, device=dev)
+    empty_w[-1] = eos_coef
+    total = 0.0
+    for qlog, mlog in levels:
+        q = qlog[0]
+        target_cls = torch.full((q.shape[0],), n_classes, dtype=torch.int64, device=dev)
+        target_cls[qi] = tgt_cls[tj]
+        l_ce = F.cross_entropy(q, target_cls, empty_w)
+        src = mlog.t()[qi]                                          # [T',P]
+        t = tgt_masks[tj]
+        T = max(len(qi), 1)
+        l_mask = _focal(src, t).mean(1).sum() / T
+        sig = src.sigmoid()
+        l_dice = (1 - (2 * (sig * t).sum(1) + 1) / (sig.sum(1) + t.sum(1) + 1)).sum() / T
+        total = total + w_ce * l_ce + w_mask * l_mask + w_dice * l_dice
+    return total
+
+
+def masks_at(coords: torch.Tensor, boxes) -> torch.Tensor:
+    """Sample box masks (pasco_b200.synthetic.make_scene) at voxel coordinates → float [T,P]."""
+    c = coords[:, 1:]
+    rows = []
+    for lo, hi in boxes:
+        rows.append(((c[:, 0] >= lo[0]) & (c[:, 0] < hi[0]) & (c[:, 1] >= lo[1]) & (c[:, 1] < hi[1])
+                     & (c[:, 2] >= lo[2]) & (c[:, 2] < hi[2])).float())
+    return torch.stack(rows)
+
+
+def total_loss(out: Dict, scene: Dict, n_classes: int, class_frequencies) -> torch.Tensor:
+    loss = completion_loss(out["sem_logits_at_scales"], scene["sem_labels"], scene["min_Cs"], class_frequencies)
+    for m, pred in enumerate(out.get("panop_predictions", [])):
+        tm = masks_at(pred["voxel_logits"].C, scene["mask_boxes"])
+        loss = loss + panoptic_set_loss(pred, scene["mask_classes"].to(tm.device), tm, n_classes) / len(out["panop_predictions"])
+    return loss

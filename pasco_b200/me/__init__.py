@@ -402,6 +402,7 @@ class _Convolution(MinkowskiModuleBase):
             (self.kernel_volume, self.in_channels, self.out_channels)
         self.kernel = nn.Parameter(torch.empty(*shape))
         self.bias = nn.Parameter(torch.empty(1, self.out_channels)) if bias else None
+        self._packs = ops.PackedWeights()
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -430,7 +431,7 @@ class _Convolution(MinkowskiModuleBase):
         else:
             out_key = in_key
         kmap = cm.kernel_map(in_key, out_key, self.kernel_size, self.stride, self.dilation, self.is_transpose)
-        out = ops.SparseConv.apply(x.F.float(), self.kernel, self.bias, kmap)
+        out = ops.SparseConv.apply(x.F.float(), self.kernel, self.bias, kmap, self._packs)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
     def extra_repr(self):

@@ -11,10 +11,18 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import call, ptr, int_array
+from ._lib import call as _raw_call, ptr, int_array
+
+
+def call(name, *args):
+    global CALLS
+    CALLS += 1
+    _raw_call(name, *args)
 
 _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
+PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
+CALLS = 0               # number of C-ABI compute calls (each launches >= 1 kernel of ours)
 
 
 def set_precision(mode) -> None:
@@ -267,24 +275,25 @@ class KernelMap:
         return self._nbr_t, self._koff_t
 
 
-_PACK_CACHE = {}
+class PackedWeights:
+    """UMMA shared-memory images of one weight tensor (forward and transposed), owned by the module
+    that owns the parameter and re-packed whenever the parameter changes (optimizer step, load_state_dict,
+    device move).  Keyed by (data_ptr, version, shape) of that one parameter only."""
 
+    def __init__(self):
+        self._slots = {}
 
-def _packed(weight: torch.Tensor, transpose: bool) -> torch.Tensor:
-    """UMMA shared-memory image of W (re-packed when the parameter changes)."""
-    key = (weight.data_ptr(), transpose)
-    ver = weight._version
-    hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[2] == tuple(weight.shape):
-        return hit[1]
-    K, Cin, Cout = weight.shape
-    nbytes = _lib.load().pasco_conv_packed_bytes(K, Cin, Cout)
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
-    call("pasco_conv_pack_weights", ptr(weight.detach().contiguous()), K, Cin, Cout, int(transpose), ptr(buf))
-    if len(_PACK_CACHE) > 4096:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (ver, buf, tuple(weight.shape))
-    return buf
+    def get(self, weight: torch.Tensor, transpose: bool) -> torch.Tensor:
+        tag = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        hit = self._slots.get(transpose)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        K, Cin, Cout = weight.shape
+        nbytes = _lib.load().pasco_conv_packed_bytes(K, Cin, Cout)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        call("pasco_conv_pack_weights", ptr(weight.detach().contiguous()), K, Cin, Cout, int(transpose), ptr(buf))
+        self._slots[transpose] = (tag, buf)
+        return buf
 
 
 def _tc_ok(c_contract: int, c_out: int, K: int) -> bool:
@@ -293,7 +302,7 @@ def _tc_ok(c_contract: int, c_out: int, K: int) -> bool:
 
 def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                transpose_w: bool, koff: Optional[Sequence[int]], bias: Optional[torch.Tensor] = None,
-               in_scale=None, in_shift=None, in_act: int = 0) -> torch.Tensor:
+               in_scale=None, in_shift=None, in_act: int = 0, packs: Optional[PackedWeights] = None) -> torch.Tensor:
     """out[o] = Σ_k act(feats·scale+shift)[nbr[k,o]] @ Wk, Wk = W[koff[k]] (transposed when transpose_w)."""
     K, Cin, Cout = weight.shape
     c_contract, c_out = (Cout, Cin) if transpose_w else (Cin, Cout)
@@ -302,9 +311,13 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
     out = torch.empty(n_out, c_out, dtype=torch.float32, device=feats.device)
     kk = nbr.shape[0] if nbr is not None else 1
     koff_arr = int_array(koff) if koff is not None else None
+    prof = PROFILE
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if _tc_ok(c_contract, c_out, kk):
         call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
-             ptr(_packed(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
+             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
              ptr(out), _PRECISION)
     else:
         assert in_scale is None and in_act == 0, "fused prologue needs the tensor-core path"
@@ -312,6 +325,12 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
             nbr = torch.arange(n_out, dtype=torch.int32, device=feats.device).view(1, -1)
         call("pasco_conv_forward_simt", ptr(feats), ptr(nbr), kk, n_out, c_contract, c_out,
              ptr(weight.detach().contiguous()), int(transpose_w), koff_arr, ptr(bias), ptr(out))
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append(("dgrad" if transpose_w else "fwd", ev0, ev1,
+                     dict(n_in=feats.shape[0], n_out=n_out, K=kk, Cin=c_contract, Cout=c_out, nbr=nbr,
+                          tc=_tc_ok(c_contract, c_out, kk), precision=_PRECISION)))
     return out
 
 
@@ -320,6 +339,10 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
     n_out = gout.shape[0]
     dW = torch.zeros(K, Cin, Cout, dtype=torch.float32, device=feats.device)
     feats, gout = feats.contiguous(), gout.contiguous()
+    prof = PROFILE
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if (not _FORCE_SIMT) and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256:
         call("pasco_conv_wgrad_tc", ptr(feats), feats.shape[0], ptr(nbr), K, n_out, Cin, Cout, ptr(gout),
              ptr(in_scale), ptr(in_shift), in_act, ptr(dW), _PRECISION)
@@ -328,6 +351,11 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
         if nbr is None:
             nbr = torch.arange(n_out, dtype=torch.int32, device=feats.device).view(1, -1)
         call("pasco_conv_wgrad_simt", ptr(feats), ptr(nbr), K, n_out, Cin, Cout, ptr(gout), ptr(dW))
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        prof.append(("wgrad", ev0, ev1, dict(n_in=feats.shape[0], n_out=n_out, K=K, Cin=Cin, Cout=Cout, nbr=nbr,
+                                             tc=True, precision=_PRECISION)))
     return dW
 
 
@@ -335,12 +363,13 @@ class SparseConv(torch.autograd.Function):
     """ME ConvolutionForward/Backward over a cached KernelMap."""
 
     @staticmethod
-    def forward(ctx, feats, weight, bias, kmap: KernelMap):
+    def forward(ctx, feats, weight, bias, kmap: KernelMap, packs: Optional[PackedWeights] = None):
         ctx.kmap = kmap
+        ctx.packs = packs
         ctx.has_bias = bias is not None
         ctx.save_for_backward(feats, weight)
         return conv_apply(feats, weight, kmap.nbr, kmap.n_out, False, None,
-                          bias.view(-1).contiguous() if bias is not None else None)
+                          bias.view(-1).contiguous() if bias is not None else None, packs=packs)
 
     @staticmethod
     def backward(ctx, g):
@@ -350,13 +379,13 @@ class SparseConv(torch.autograd.Function):
         gin = gw = gb = None
         if ctx.needs_input_grad[0]:
             nbr_t, koff_t = kmap.transposed()
-            gin = conv_apply(g, weight, nbr_t, kmap.n_in, True, koff_t)
+            gin = conv_apply(g, weight, nbr_t, kmap.n_in, True, koff_t, packs=ctx.packs)
         if ctx.needs_input_grad[1]:
             K, Cin, Cout = weight.shape
             gw = conv_wgrad(feats, g, kmap.nbr, K, Cin, Cout)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0, keepdim=True)
-        return gin, gw, gb, None
+        return gin, gw, gb, None, None
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,39 @@
+"""Synthetic scenes for BASELINE.json's configs: Bernoulli occupancy on an X×Y×Z grid,
+one point per occupied voxel, N(0,1) point features, identity pose, labels uniform over classes with
+p(empty)=0.9.  CPU tensors (pin + copy them yourself); deterministic in `seed`."""
+from __future__ import annotations
+
+from typing import Dict, Sequence
+
+import torch
+
+
+def make_scene(grid: Sequence[int] = (256, 256, 32), occ: float = 0.10, n_infers: int = 1, in_ch: int = 283,
+               n_classes: int = 20, seed: int = 0, n_masks: int = 10) -> Dict:
+    g = torch.Generator().manual_seed(seed)
+    X, Y, Z = grid
+    b: Dict = {"in_feats": [], "in_coords": [], "min_Cs": [], "max_Cs": [], "Ts": []}
+    for _ in range(n_infers):
+        o = torch.rand(X, Y, Z, generator=g) < occ
+        c = torch.nonzero(o).int()
+        b["in_coords"].append(c)
+        b["in_feats"].append(torch.randn(c.shape[0], in_ch, generator=g))
+        b["min_Cs"].append(torch.tensor([0, 0, 0]))
+        b["max_Cs"].append(torch.tensor([X - 1, Y - 1, Z - 1]))
+        b["Ts"].append(torch.eye(4))
+    b["global_min_Cs"] = torch.tensor([0, 0, 0])
+    b["global_max_Cs"] = torch.tensor([X - 1, Y - 1, Z - 1])
+    sem = {}
+    for s in (1, 2, 4):
+        lab = torch.randint(1, n_classes, (n_infers, X // s, Y // s, Z // s), generator=g)
+        lab[torch.rand(lab.shape, generator=g) < 0.9] = 0
+        sem[f"1_{s}"] = lab.to(torch.uint8)
+    b["sem_labels"] = sem
+    # instance masks: random boxes (dense bool [n_masks, X, Y, Z]) with a thing/stuff class each
+    boxes = []
+    for _ in range(n_masks):
+        lo = [int(torch.randint(0, d - d // 4, (1,), generator=g)) for d in (X, Y, Z)]
+        boxes.append((lo, [min(d, l + max(2, d // 4)) for l, d in zip(lo, (X, Y, Z))]))
+    b["mask_boxes"] = boxes
+    b["mask_classes"] = torch.randint(1, n_classes, (n_masks,), generator=g)
+    return b

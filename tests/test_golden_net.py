@@ -1,0 +1,101 @@
+"""Pins pasco_b200.net3d (the engine-native restatement of PaSCo's hot path) against golden vectors
+produced by the UNMODIFIED reference running on the CPU oracle (tests/golden/make_golden.py).
+
+CPU part : parameter names / shapes equal the reference's state_dict manifest (checkpoint drop-in).
+GPU part : same recipe weights + same synthetic scene → sem logits at 3 scales, query logits and mask
+           logits agree with the golden subsample within the north_star tolerance (1e-3, max-abs
+           normalised).  Coordinate sets must be identical up to argmax near-ties (≤ 0.1 % of rows).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from recipe import fill_state_dict  # noqa: E402
+
+MANIFEST = json.load(open(os.path.join(HERE, "golden", "net_cfg1_manifest.json")))
+
+
+def _net():
+    from pasco_b200.net3d import PascoNet
+    torch.manual_seed(0)
+    return PascoNet(n_classes=20, n_infers=1, in_channels=283, f=64, num_queries=100, heavy_decoder=False)
+
+
+def test_state_dict_names_and_shapes_match_the_reference():
+    sd = _net().reference_state_dict()
+    mine = {k: list(v.shape) for k, v in sd.items()}
+    ref = MANIFEST["params"]
+    assert sorted(mine) == sorted(ref), (sorted(set(ref) - set(mine))[:5], sorted(set(mine) - set(ref))[:5])
+    bad = [k for k in ref if mine[k] != ref[k]]
+    assert not bad, bad[:5]
+    assert sum(int(np.prod(s)) for s in ref.values()) > 100e6
+
+
+def test_reference_state_dict_round_trip():
+    net = _net()
+    sd = fill_state_dict(net.reference_state_dict())
+    net.load_reference_state_dict(sd)
+    back = net.reference_state_dict()
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+    with pytest.raises(KeyError):
+        net.load_reference_state_dict({k: v for k, v in sd.items() if "enc_in_feats" not in k})
+
+
+def _keys(C):
+    c = torch.as_tensor(np.asarray(C, dtype=np.int64))
+    return ((c[:, 0] + 32768) << 48) | ((c[:, 1] + 32768) << 32) | ((c[:, 2] + 32768) << 16) | (c[:, 3] + 32768)
+
+
+def _compare(name, got_C, got_F, gold_C, gold_F_sub, step, tol=1e-3):
+    gk, rk = _keys(got_C.cpu().numpy()), _keys(gold_C)
+    order = torch.argsort(gk)
+    gk, gF = gk[order], got_F.detach().cpu()[order]
+    common = np.intersect1d(gk.numpy(), rk.numpy())
+    sym = (len(gk) - len(common)) + (len(rk) - len(common))
+    assert sym <= max(2, 0.001 * len(rk)), f"{name}: coordinate sets differ in {sym} of {len(rk)} rows"
+    sub_keys = rk[::step]
+    pos = torch.searchsorted(gk, sub_keys).clamp(max=len(gk) - 1)
+    hit = gk[pos] == sub_keys
+    ref = torch.as_tensor(gold_F_sub)[hit]
+    got = gF[pos[hit]]
+    err = float((got.double() - ref.double()).abs().max() / ref.double().abs().max())
+    assert err <= tol, f"{name}: feature error {err:.3e} > {tol}"
+    return sym, err
+
+
+@pytest.mark.gpu
+def test_full_forward_matches_reference_golden():
+    from pasco_b200 import ops
+    from pasco_b200.synthetic import make_scene
+    ops.set_precision("fp32")
+    gold = np.load(os.path.join(HERE, "golden", "net_cfg1.npz"))
+    net = _net()
+    net.load_reference_state_dict(fill_state_dict(net.reference_state_dict()))
+    net.cuda().train()
+    b = make_scene(MANIFEST["grid"], MANIFEST["occ"], 1, seed=MANIFEST["seed"])
+    dev = torch.device("cuda")
+    with torch.no_grad():
+        out = net([f.to(dev) for f in b["in_feats"]], [c.to(dev) for c in b["in_coords"]],
+                  b["global_min_Cs"], b["global_max_Cs"], b["min_Cs"], b["max_Cs"])
+    step = MANIFEST["row_step"]
+    report = {}
+    for s in (4, 2, 1):
+        lg = out["sem_logits_at_scales"][s][0]
+        report[f"sem{s}"] = _compare(f"sem{s}", lg.C, lg.F, gold[f"sem{s}_C"], gold[f"sem{s}_F"], step)
+    p = out["panop_predictions"][0]
+    report["vox"] = _compare("voxel_logits", p["voxel_logits"].C, p["voxel_logits"].F, gold["vox_C"], gold["vox_F"], step)
+    q = p["query_logits"][0].cpu()
+    eq = float((q.double() - torch.as_tensor(gold["query_logits"]).double()).abs().max()
+               / np.abs(gold["query_logits"]).max())
+    assert eq <= 1e-3, f"query logits error {eq:.3e}"
+    for i, aux in enumerate(p["aux_outputs"]):
+        ea = float((aux["query_logits"][0].cpu().double() - torch.as_tensor(gold[f"aux{i}_query_logits"]).double()).abs().max()
+                   / np.abs(gold[f"aux{i}_query_logits"]).max())
+        assert ea <= 1e-3, f"aux {i} query logits error {ea:.3e}"
+    print("golden parity:", report, "query", eq)

@@ -70,10 +70,11 @@ def main():
             F = torch.randn(N, ch, device=dev)
             W = torch.randn(27, ch, ch, device=dev) * 0.05
             G = torch.randn(N, ch, device=dev)
+            pk = ops.PackedWeights()
             for prec in ("fp32", "bf16"):
                 ops.set_precision(prec)
-                fwd = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None), flush=flush)
-                dgr = timed(lambda: ops.conv_apply(G, W, nbr, N, True, [26 - k for k in range(27)]), flush=flush)
+                fwd = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk), flush=flush)
+                dgr = timed(lambda: ops.conv_apply(G, W, nbr, N, True, [26 - k for k in range(27)], packs=pk), flush=flush)
                 wgr = timed(lambda: ops.conv_wgrad(F, G, nbr, 27, ch, ch), flush=flush)
                 flops = 2.0 * pairs * ch * ch
                 dense_flops = 2.0 * N * 27 * ch * ch
