@@ -30,8 +30,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import faulthandler  # noqa: E402
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
+
+faulthandler.enable()
+_T0 = time.time()
+
+
+def log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 GRID, OCC, IN_CH, N_CLASSES = (256, 256, 32), 0.10, 283, 20
 METRIC = "scenes/sec (256x256x32 voxels @10% occ) fwd+bwd"
@@ -187,8 +197,13 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), last
 
+    log(f"model + {n_pool} scenes ready")
     for i in range(a.warmup):
+        faulthandler.dump_traceback_later(240, exit=False)
         step(dev_scenes[i % n_pool])
+        torch.cuda.synchronize()
+        faulthandler.cancel_dump_traceback_later()
+        log(f"warm-up step {i} done, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -197,7 +212,9 @@ def run_ours(a):
     ms, _ = timed(a.steps, from_host=False)
     launches = ops.CALLS - calls0
     prof, ops.PROFILE = ops.PROFILE, None
+    log(f"device-resident region: {ms / a.steps:.1f} ms/step")
     ms_e2e, _ = timed(a.steps, from_host=True)
+    log(f"e2e region: {ms_e2e / a.steps:.1f} ms/step")
     clocks = sampler.stop() if sampler else None
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event durations recorded inside the timed region) ----
@@ -253,8 +270,9 @@ def cpu_baseline(budget_s: float = 20.0):
     """CPU restatement of the ME algorithm (oracle/) on a bounded crop of the same workload, all host cores."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import net_oracle
-    cores = os.cpu_count()
+    cores = min(os.cpu_count(), 32)     # the per-offset gather/GEMM/scatter loop stops scaling beyond ~32 threads
     torch.set_num_threads(cores)
+    log(f"cpu baseline on {cores} threads ...")
     r = net_oracle.time_crop(budget_s)
     return {"value": r["scenes_per_s"], "unit": "scenes/s", "cores": cores, "kind": "port",
             "sample": r["sample"], "seconds": r["seconds"],
@@ -268,7 +286,7 @@ def run_reference(a):
     steps, warm = max(a.steps, 1), a.warmup
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import net_oracle
-    cores = os.cpu_count()
+    cores = min(os.cpu_count(), 32)
     torch.set_num_threads(cores)
     per = max(2.0, min(20.0, 120.0 / (steps + warm)))
     for _ in range(min(warm, 1)):

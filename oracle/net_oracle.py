@@ -224,7 +224,7 @@ def time_crop(budget_s: float = 20.0, full_grid=(256, 256, 32), occ=0.10):
     options = [((32, 32, 32), 64), ((64, 32, 32), 32), ((64, 64, 32), 16), ((128, 64, 32), 8)]
     grid, div = options[0]
     for g, d in options:
-        if 450.0 / d * max(0.25, 8.0 / max(os.cpu_count(), 1)) <= budget_s:
+        if 450.0 / d * max(0.5, 8.0 / max(torch.get_num_threads(), 1)) <= budget_s:
             grid, div = g, d
     torch.manual_seed(0)
     net = OracleNet(caps=tuple(max(8, c // div) for c in (25000, 120000, 400000))).train()

@@ -29,6 +29,10 @@ def set_precision(mode) -> None:
     """'fp32' (bf16x3 split operands, ~2^-16 relative) or 'bf16' (single bf16 MMA)."""
     global _PRECISION
     _PRECISION = {"fp32": 3, "bf16": 1, 3: 3, 1: 1}[mode]
+    # library ops on the path (cuDNN dense bottleneck, cuBLAS 1x1 convs / projections) follow the same contract:
+    # fp32 mode = no TF32 anywhere, bf16 mode = TF32 allowed for the library GEMMs/convs
+    torch.backends.cudnn.allow_tf32 = _PRECISION == 1
+    torch.backends.cuda.matmul.allow_tf32 = _PRECISION == 1
 
 
 def get_precision() -> int:
