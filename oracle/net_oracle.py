@@ -202,7 +202,7 @@ class OracleNet(nn.Module):
             kv = (self.input_projs[i](src.F) + self.pe(src.C[:, 1:], self.d // 3)).unsqueeze(0)
             m = self.attn_mask(msk, vox, src, s, lo, hi)
             qn = self.cross_norm[i](out)
-            out = out + self.cross[i](qn + qpos, kv, kv, attn_mask=m.unsqueeze(0).repeat(8, 1, 1))[0]
+            out = qn + self.cross[i](qn + qpos, kv, kv, attn_mask=m.unsqueeze(0).repeat(8, 1, 1))[0]   # blocks.py:82,91
             out = self.self_norm[i](out + self.selfa[i](out + qpos, out + qpos, out)[0])
             out = out + self.ffn[i](self.ffn_norm[i](out))
             cls_l, msk = self.heads(out, voxel_feat)

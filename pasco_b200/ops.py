@@ -21,6 +21,7 @@ def call(name, *args):
 
 _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
+_SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} forced onto the CUDA-core path
 PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
 CALLS = 0               # number of C-ABI compute calls (each launches >= 1 kernel of ours)
 
@@ -39,9 +40,10 @@ def get_precision() -> int:
     return _PRECISION
 
 
-def force_simt(flag: bool) -> None:
-    global _FORCE_SIMT
-    _FORCE_SIMT = bool(flag)
+def force_simt(flag: bool, kinds=None) -> None:
+    global _FORCE_SIMT, _SIMT_KINDS
+    _FORCE_SIMT = bool(flag) and kinds is None
+    _SIMT_KINDS = set(kinds) if (flag and kinds is not None) else None
 
 
 def _i32(t: torch.Tensor) -> torch.Tensor:
@@ -300,7 +302,9 @@ class PackedWeights:
         return buf
 
 
-def _tc_ok(c_contract: int, c_out: int, K: int) -> bool:
+def _tc_ok(c_contract: int, c_out: int, K: int, kind: str = "fwd") -> bool:
+    if _SIMT_KINDS is not None and kind in _SIMT_KINDS:
+        return False
     return (not _FORCE_SIMT) and c_contract % 64 == 0 and c_out % 16 == 0 and 16 <= c_out <= 256 and K <= 32
 
 
@@ -319,7 +323,8 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if _tc_ok(c_contract, c_out, kk):
+    use_tc = _tc_ok(c_contract, c_out, kk, "dgrad" if transpose_w else "fwd")
+    if use_tc:
         call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
              ptr(out), _PRECISION)
@@ -334,7 +339,7 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         ev1.record()
         prof.append(("dgrad" if transpose_w else "fwd", ev0, ev1,
                      dict(n_in=feats.shape[0], n_out=n_out, K=kk, Cin=c_contract, Cout=c_out, nbr=nbr,
-                          tc=_tc_ok(c_contract, c_out, kk), precision=_PRECISION)))
+                          tc=use_tc, precision=_PRECISION)))
     return out
 
 
@@ -347,7 +352,7 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if (not _FORCE_SIMT) and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256:
+    if _tc_ok(Cin, 64, 1, "wgrad") and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256:
         call("pasco_conv_wgrad_tc", ptr(feats), feats.shape[0], ptr(nbr), K, n_out, Cin, Cout, ptr(gout),
              ptr(in_scale), ptr(in_shift), in_act, ptr(dW), _PRECISION)
     else:

@@ -225,6 +225,15 @@ def test_conv_cuda_core_path(ME, kind, cin, cout):
         ops.force_simt(False)
 
 
+def test_conv_many_tiles_per_cta(ME):
+    """~59k voxels: every persistent CTA walks several 128-row tiles (and several 64-row wgrad tiles
+    accumulating in TMEM), unlike the small cases above."""
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    e = _run_conv_case(ME, "k3", 64, 64, TOL_TIGHT, shape=(64, 64, 32), p=0.225)
+    print(f"bf16x3 k3 64->64 @59k rows: fwd {e[0]:.2e} dgrad {e[1]:.2e} wgrad {e[2]:.2e}")
+
+
 def test_conv_tile_tail_and_single_voxel(ME):
     """n_out not a multiple of the 128-row tile, and a 1-voxel tensor."""
     from pasco_b200 import ops
@@ -343,11 +352,11 @@ def _mini_net(M):
     return Net()
 
 
-@pytest.mark.parametrize("simt", [False, True])
+@pytest.mark.parametrize("simt", [None, "all", "fwd", "dgrad", "wgrad"])
 def test_unet_slice_forward_backward_matches_oracle(ME, simt):
     from pasco_b200 import ops
     ops.set_precision("fp32")
-    ops.force_simt(simt)
+    ops.force_simt(simt is not None, None if simt in (None, "all") else [simt])
     torch.manual_seed(0)
     rnet = _mini_net(OR)
     gnet = _mini_net(ME)
