@@ -369,6 +369,16 @@ def test_unet_slice_forward_backward_matches_oracle(ME, simt):
     (ry.F ** 2).mean().backward()
     (gy.F ** 2).mean().backward()
     ops.force_simt(False)
-    errs = {n: relerr(pg.grad, pr.grad) for (n, pr), (_, pg) in zip(rnet.named_parameters(), gnet.named_parameters())}
-    print(f"unet slice (simt={simt}): fwd {e:.2e}; param-grad errors: " + ", ".join(f"{n}={v:.1e}" for n, v in errs.items()))
-    assert max(errs.values()) <= 2e-2, max(errs, key=errs.get)
+    # Gradients flow through ReLU masks: a forward difference of 1e-5 flips the sign of a handful of
+    # pre-activations (out of ~1e5), each flip moving a parameter gradient by ~1/sqrt(rows*K) of its
+    # max — so judge gradients in the relative L2 norm (robust to single flips), max-norm only loosely.
+    def l2(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).norm() / b.norm().clamp(min=1e-30))
+    errs = {n: (l2(pg.grad, pr.grad), relerr(pg.grad, pr.grad))
+            for (n, pr), (_, pg) in zip(rnet.named_parameters(), gnet.named_parameters())}
+    worst = max(errs, key=lambda n: errs[n][0])
+    print(f"unet slice (simt={simt}): fwd {e:.2e}; worst param-grad rel-L2 {errs[worst][0]:.1e} ({worst}), "
+          f"worst max-norm {max(v[1] for v in errs.values()):.1e}")
+    assert errs[worst][0] <= 1e-3, worst
+    assert max(v[1] for v in errs.values()) <= 2e-2
