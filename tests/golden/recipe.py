@@ -7,10 +7,19 @@ import zlib
 import torch
 
 
+def _canonical(name: str) -> str:
+    """The reference registers its one transformer under three names (Net.transformer_predictor,
+    unet3d.transformer_predictor, unet3d.decoder_generative.transformer_predictor): seed them identically."""
+    for alias in ("unet3d.decoder_generative.transformer_predictor.", "unet3d.transformer_predictor."):
+        if name.startswith(alias):
+            return "transformer_predictor." + name[len(alias):]
+    return name
+
+
 def fill_state_dict(sd):
     out = {}
     for name, t in sd.items():
-        g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+        g = torch.Generator().manual_seed(zlib.crc32(_canonical(name).encode()))
         if not t.dtype.is_floating_point:
             out[name] = torch.zeros_like(t)
             continue
