@@ -3,15 +3,19 @@
 //   out[o, :] = Σ_k  in[nbr[k, o], :] @ W[k]           (output-stationary implicit GEMM)
 //
 // One persistent CTA per SM walks 128-row output tiles.  Warp roles:
-//   warps 0-3  gather: for every (offset k, 64-channel block) load the neighbour rows of the tile from HBM/L2
-//              (coalesced 16-byte loads, 16 lanes per 256-byte row segment), optionally apply the fused
-//              BatchNorm affine + activation of the producing layer, split fp32 → bf16 hi (+ lo), and store the
-//              128x64 tile into shared memory in the 128-byte-swizzled K-major UMMA layout.  Lane 0 of warp 0
-//              also streams the pre-swizzled weight slice W[k] with one bulk async copy (UBLKCP).
-//   warp  8    one elected thread issues tcgen05.mma (M=128, N=Cout, K=16) into a TMEM accumulator and
-//              commits to the stage's "empty" mbarrier; the accumulator is double-buffered in TMEM so the
-//              epilogue of tile t overlaps the main loop of tile t+1.
-//   warps 4-7  epilogue: tcgen05.ld the accumulator (lane = output row), add bias, store fp32 rows.
+// A CTA owns a GROUP of T = 256/Cout consecutive tiles whose accumulators live side by side in TMEM, and walks
+// group → offset k → 64-channel block → tile, so every weight slice W[k] is fetched from L2 once per group
+// instead of once per tile.
+//   warps 0-3  gather: load the neighbour rows of a tile (coalesced 16-byte loads, 16 lanes per 256-byte row
+//              segment; neighbour indices arrive through a cp.async ring one offset ahead), optionally apply
+//              the fused BatchNorm affine + activation of the producing layer, split fp32 → bf16 hi (+ lo), and
+//              store the 128x64 tile into shared memory in the 128-byte-swizzled K-major UMMA layout.  Loads of
+//              slot s+1 are in flight in registers while slot s is converted and stored.
+//   warp  9    streams the pre-swizzled weight slices with bulk async copies (UBLKCP) into their own ring.
+//   warp  8    one elected thread issues tcgen05.mma (M=128, N=Cout, K=16) into the tile's TMEM accumulator
+//              and commits to the A / B "empty" mbarriers; accumulator sets are double-buffered in TMEM so
+//              the epilogue of group g overlaps the main loop of group g+1.
+//   warps 4-7  epilogue: tcgen05.ld the accumulators (lane = output row), add bias, store fp32 rows.
 // No atomics: every output row is written exactly once, results are run-to-run deterministic.
 //
 // precision 3 (the "fp32" mode): operands split as x = hi + lo (bf16 each) and three MMAs
@@ -29,7 +33,9 @@ constexpr int KBLK = 64;                    // channels per K-block (= one 128-b
 constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB
 constexpr int NUM_GATHER_WARPS = 4;
 constexpr int NUM_EPI_WARPS = 4;
-constexpr int NUM_THREADS = (NUM_GATHER_WARPS + NUM_EPI_WARPS + 1) * 32;  // 288
+constexpr int MMA_WARP = NUM_GATHER_WARPS + NUM_EPI_WARPS;      // 8
+constexpr int LOAD_WARP = MMA_WARP + 1;                        // 9
+constexpr int NUM_THREADS = (LOAD_WARP + 1) * 32;              // 320
 constexpr int MAX_STAGES = 8;
 
 struct ConvParams {
@@ -43,7 +49,7 @@ struct ConvParams {
   int64_t n_out;
   int64_t out_pitch;
   int K, Cin, Cout, in_act;
-  int stages, tmem_cols;
+  int sa, sb, tiles_per_group, tmem_cols;
   int koff[32];
 };
 
@@ -91,37 +97,68 @@ __device__ __forceinline__ float act_apply(float z, int act) {
   return z;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// cp.async helpers for the neighbour-index ring
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int IDX_RING = 4;  // neighbour-index ring depth (entries of T*128 ints, one per (tile group, offset))
+
+// position of a gather warp inside the flat slot sequence  group → k → kb → t
+struct SlotIt {
+  int64_t group;   // tile group handled by this CTA
+  int gk;          // running (group, k) counter → index ring slot
+  int k, kb, t;
+  int t_eff;       // tiles in this group
+  bool valid;
+};
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: stages x [A_hi | A_lo? | B_hi | B_lo?], then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int n_op = (NSPLIT == 3) ? 2 : 1;
   const int b_tile = p.Cout * 128;
-  const int n_op = (NSPLIT == 3) ? 2 : 1;
-  const int stage_bytes = n_op * (A_TILE_BYTES + b_tile);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* full_bar = bars;                      // [stages]
-  uint64_t* empty_bar = bars + MAX_STAGES;        // [stages]
-  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;    // [2]
-  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const int a_stage_bytes = n_op * A_TILE_BYTES;
+  const int b_stage_bytes = n_op * b_tile;
+  const int T = p.tiles_per_group;
+  uint8_t* a_smem = smem;                                           // [sa][A_hi | A_lo]
+  uint8_t* b_smem = smem + (size_t)p.sa * a_stage_bytes;            // [sb][B_hi | B_lo]
+  int* idx_ring = reinterpret_cast<int*>(b_smem + (size_t)p.sb * b_stage_bytes);   // [IDX_RING][T*128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_ring + IDX_RING * T * BLOCK_M);
+  uint64_t* afull = bars;                         // [MAX_STAGES]
+  uint64_t* aempty = bars + MAX_STAGES;           // [MAX_STAGES]
+  uint64_t* bfull = bars + 2 * MAX_STAGES;        // [MAX_STAGES]
+  uint64_t* bempty = bars + 3 * MAX_STAGES;       // [MAX_STAGES]
+  uint64_t* tfull = bars + 4 * MAX_STAGES;        // [2]
+  uint64_t* tempty = bars + 4 * MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.Cin / KBLK;
   const int64_t num_tiles = (p.n_out + BLOCK_M - 1) / BLOCK_M;
+  const int64_t num_groups = (num_tiles + T - 1) / T;
+  const int acc_cols = T * p.Cout;                // TMEM columns of one accumulator set
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(full_bar + s), NUM_GATHER_WARPS + 1);
-      mbar_init(smem_u32(empty_bar + s), 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(smem_u32(afull + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(aempty + s), 1);
+      mbar_init(smem_u32(bfull + s), 1);
+      mbar_init(smem_u32(bempty + s), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(tfull_bar + b), 1);
-      mbar_init(smem_u32(tempty_bar + b), NUM_EPI_WARPS);
+      mbar_init(smem_u32(tfull + b), 1);
+      mbar_init(smem_u32(tempty + b), NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -129,168 +166,282 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 
   if (warp < NUM_GATHER_WARPS) {
     // ===================================== gather producers =====================================
-    int stage = 0;
-    uint32_t phase = 0;
-    const int chunk = lane & 15;   // 16-byte fp32 chunk inside the 64-channel block
-    const int rsub = lane >> 4;    // which of the 2 rows this half-warp handles per step
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int64_t row0 = tile * BLOCK_M + warp * 32;
-      for (int k = 0; k < p.K; ++k) {
-        int64_t my_row = row0 + lane;
-        int idx = -1;
-        if (my_row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + my_row) : (int)my_row;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-          uint8_t* st = smem + (size_t)stage * stage_bytes;
-          if (warp == 0 && lane == 0) {
-            const uint32_t bytes = (uint32_t)(n_op * b_tile);
-            mbar_arrive_expect_tx(smem_u32(full_bar + stage), bytes);
-            const uint8_t* src = p.wpk + ((int64_t)p.koff[k] * KB + kb) * (int64_t)p.Cout * 256;
-            bulk_g2s(smem_u32(st + n_op * A_TILE_BYTES), src, bytes, smem_u32(full_bar + stage));
-          }
-          const int cbase = kb * KBLK + chunk * 4;
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool affine = p.in_scale != nullptr;
-          if (affine) {
-            sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + cbase));
-            sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + cbase));
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 v[8];
-            int srcs[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              int r = (half * 8 + i) * 2 + rsub;
-              srcs[i] = __shfl_sync(0xffffffffu, idx, r);
-              v[i] = srcs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)srcs[i] * p.Cin + cbase))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              int r = (half * 8 + i) * 2 + rsub;
-              float4 x = v[i];
-              if (affine || p.in_act) {
-                if (srcs[i] >= 0) {
-                  x.x = act_apply(fmaf(x.x, sc.x, sh.x), p.in_act);
-                  x.y = act_apply(fmaf(x.y, sc.y, sh.y), p.in_act);
-                  x.z = act_apply(fmaf(x.z, sc.z, sh.z), p.in_act);
-                  x.w = act_apply(fmaf(x.w, sc.w, sh.w), p.in_act);
-                }
-              }
-              const int trow = warp * 32 + r;
-              const uint32_t off = (uint32_t)trow * 128u + (uint32_t)(((chunk >> 1) ^ (trow & 7)) << 4) + (uint32_t)((chunk & 1) << 3);
-              uint2 hi, lo;
-              split4(x, hi, lo);
-              *reinterpret_cast<uint2*>(st + off) = hi;
-              if (NSPLIT == 3) *reinterpret_cast<uint2*>(st + A_TILE_BYTES + off) = lo;
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+    const int chunk = lane & 15;  // 16-byte fp32 chunk inside the 64-channel block
+    const int rsub = lane >> 4;   // which of the 2 rows this half-warp handles per step
+    const bool affine = p.in_scale != nullptr;
+
+    // async prefetch of the neighbour indices of (group, k) into ring slot gk % IDX_RING: this warp's 32 rows of
+    // each of the group's tiles
+    auto prefetch_idx = [&](int64_t group, int k, int gk, int t_eff) {
+      int* dst = idx_ring + (gk % IDX_RING) * T * BLOCK_M;
+      for (int t = 0; t < t_eff; ++t) {
+        const int64_t row = (group * T + t) * BLOCK_M + warp * 32 + lane;
+        int* d = dst + t * BLOCK_M + warp * 32 + lane;
+        if (row < p.n_out) {
+          if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
+          else *d = (int)row;
+        } else {
+          *d = -1;
         }
       }
+      cp_async_commit();
+    };
+    auto advance = [&](SlotIt& it) {
+      if (++it.t < it.t_eff) return;
+      it.t = 0;
+      if (++it.kb < KB) return;
+      it.kb = 0;
+      ++it.gk;
+      if (++it.k < p.K) return;
+      it.k = 0;
+      it.group += gridDim.x;
+      it.valid = it.group < num_groups;
+      if (it.valid) {
+        int64_t rem = num_tiles - it.group * T;
+        it.t_eff = rem < T ? (int)rem : T;
+      }
+    };
+    // the (group,k) pair that follows `it`'s by `ahead` steps, for index prefetch
+    auto prefetch_ahead = [&](const SlotIt& it, int ahead) {
+      int64_t g = it.group;
+      int k = it.k + ahead, gk = it.gk + ahead;
+      while (k >= p.K) {
+        k -= p.K;
+        g += gridDim.x;
+      }
+      if (g < num_groups) {
+        int64_t rem = num_tiles - g * T;
+        prefetch_idx(g, k, gk, rem < T ? (int)rem : T);
+      } else {
+        cp_async_commit();  // keep the group count uniform
+      }
+    };
+
+    SlotIt ld;
+    ld.group = blockIdx.x; ld.gk = 0; ld.k = 0; ld.kb = 0; ld.t = 0;
+    ld.valid = ld.group < num_groups;
+    if (ld.valid) {
+      int64_t rem = num_tiles - ld.group * T;
+      ld.t_eff = rem < T ? (int)rem : T;
+      // prime the index ring: entries 0 .. IDX_RING-2
+      for (int a = 0; a < IDX_RING - 1; ++a) prefetch_ahead(ld, a);
     }
-  } else if (warp == 8) {
-    // ===================================== MMA issuer =====================================
+    SlotIt st = ld;
+    int stage = 0;
+    uint32_t phase = 0;
+
+    float4 va[16], vb[16];
+    uint32_t valid_a = 0, valid_b = 0;
+
+    // issue the 16 row-segment loads of one slot into registers
+    auto issue = [&](SlotIt& it, float4 (&v)[16], uint32_t& valid) {
+      if (it.kb == 0 && it.t == 0) {
+        // first use of ring entry gk: it was prefetched IDX_RING-1 entries ago; keep the ring primed
+        cp_async_wait<IDX_RING - 2>();
+        __syncwarp();
+        prefetch_ahead(it, IDX_RING - 1);
+      }
+      const int* irow = idx_ring + (it.gk % IDX_RING) * T * BLOCK_M + it.t * BLOCK_M + warp * 32;
+      const int cbase = it.kb * KBLK + chunk * 4;
+      valid = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int src = irow[i * 2 + rsub];
+        if (src >= 0) {
+          v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)src * p.Cin + cbase));
+          valid |= 1u << i;
+        } else {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    // convert + store one slot into its A stage and publish it
+    auto store = [&](const SlotIt& it, float4 (&v)[16], uint32_t valid) {
+      mbar_wait(smem_u32(aempty + stage), phase ^ 1);
+      uint8_t* dst = a_smem + (size_t)stage * a_stage_bytes;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (affine) {
+        const int cbase = it.kb * KBLK + chunk * 4;
+        sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + cbase));
+        sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + cbase));
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float4 x = v[i];
+        if ((affine || p.in_act) && ((valid >> i) & 1u)) {
+          x.x = act_apply(fmaf(x.x, sc.x, sh.x), p.in_act);
+          x.y = act_apply(fmaf(x.y, sc.y, sh.y), p.in_act);
+          x.z = act_apply(fmaf(x.z, sc.z, sh.z), p.in_act);
+          x.w = act_apply(fmaf(x.w, sc.w, sh.w), p.in_act);
+        }
+        const int trow = warp * 32 + i * 2 + rsub;
+        const uint32_t off = (uint32_t)trow * 128u + (uint32_t)(((chunk >> 1) ^ (trow & 7)) << 4) + (uint32_t)((chunk & 1) << 3);
+        uint2 hi, lo;
+        split4(x, hi, lo);
+        *reinterpret_cast<uint2*>(dst + off) = hi;
+        if (NSPLIT == 3) *reinterpret_cast<uint2*>(dst + A_TILE_BYTES + off) = lo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(afull + stage));
+      if (++stage == p.sa) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+
+    if (ld.valid) {
+      issue(ld, va, valid_a);
+      advance(ld);
+      while (st.valid) {
+        if (ld.valid) {
+          issue(ld, vb, valid_b);
+          advance(ld);
+        }
+        store(st, va, valid_a);
+        advance(st);
+        if (!st.valid) break;
+        if (ld.valid) {
+          issue(ld, va, valid_a);
+          advance(ld);
+        }
+        store(st, vb, valid_b);
+        advance(st);
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == LOAD_WARP) {
+    // ===================================== weight-slice loader =====================================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.Cout, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(smem_u32(tempty_bar + buf), ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.Cout);
-        uint32_t accum = 0;
+      const uint32_t bytes = (uint32_t)b_stage_bytes;
+      for (int64_t group = blockIdx.x; group < num_groups; group += gridDim.x) {
         for (int k = 0; k < p.K; ++k) {
           for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(smem_u32(full_bar + stage), phase);
-            tc_fence_after();
-            const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
-            const uint32_t b_hi = st + n_op * A_TILE_BYTES, b_lo = b_hi + b_tile;
-#pragma unroll
-            for (int j = 0; j < KBLK / 16; ++j) {
-              const uint64_t da_hi = make_desc_sw128(a_hi + j * 32, 16, 1024);
-              const uint64_t db_hi = make_desc_sw128(b_hi + j * 32, 16, 1024);
-              mma_bf16(d_tmem, da_hi, db_hi, idesc, accum);
-              accum = 1;
-              if (NSPLIT == 3) {
-                const uint64_t da_lo = make_desc_sw128(a_lo + j * 32, 16, 1024);
-                const uint64_t db_lo = make_desc_sw128(b_lo + j * 32, 16, 1024);
-                mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
-                mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-              }
+            mbar_wait(smem_u32(bempty + stage), phase ^ 1);
+            mbar_arrive_expect_tx(smem_u32(bfull + stage), bytes);
+            const uint8_t* src = p.wpk + ((int64_t)p.koff[k] * KB + kb) * (int64_t)p.Cout * 256;
+            if (NSPLIT == 3) {
+              bulk_g2s(smem_u32(b_smem + (size_t)stage * b_stage_bytes), src, bytes, smem_u32(bfull + stage));
+            } else {
+              bulk_g2s(smem_u32(b_smem + (size_t)stage * b_stage_bytes), src, bytes, smem_u32(bfull + stage));
             }
-            mma_commit(smem_u32(empty_bar + stage));
-            if (++stage == p.stages) {
+            if (++stage == p.sb) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        mma_commit(smem_u32(tfull_bar + buf));
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.Cout, 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int64_t group = blockIdx.x; group < num_groups; group += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int64_t rem = num_tiles - group * T;
+        const int t_eff = rem < T ? (int)rem : T;
+        mbar_wait(smem_u32(tempty + buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int k = 0; k < p.K; ++k) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(smem_u32(bfull + sb), pb);
+            const uint32_t b_hi = smem_u32(b_smem + (size_t)sb * b_stage_bytes), b_lo = b_hi + b_tile;
+            for (int t = 0; t < t_eff; ++t) {
+              mbar_wait(smem_u32(afull + sa), pa);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(a_smem + (size_t)sa * a_stage_bytes), a_lo = a_hi + A_TILE_BYTES;
+              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_cols + t * p.Cout);
+#pragma unroll
+              for (int j = 0; j < KBLK / 16; ++j) {
+                const uint32_t accum = (k > 0 || kb > 0 || j > 0) ? 1u : 0u;
+                const uint64_t da_hi = make_desc_sw128(a_hi + j * 32, 16, 1024);
+                const uint64_t db_hi = make_desc_sw128(b_hi + j * 32, 16, 1024);
+                mma_bf16(d_tmem, da_hi, db_hi, idesc, accum);
+                if (NSPLIT == 3) {
+                  const uint64_t da_lo = make_desc_sw128(a_lo + j * 32, 16, 1024);
+                  const uint64_t db_lo = make_desc_sw128(b_lo + j * 32, 16, 1024);
+                  mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
+                  mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+                }
+              }
+              mma_commit(smem_u32(aempty + sa));
+              if (++sa == p.sa) {
+                sa = 0;
+                pa ^= 1;
+              }
+            }
+            mma_commit(smem_u32(bempty + sb));
+            if (++sb == p.sb) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+        }
+        mma_commit(smem_u32(tfull + buf));
       }
     }
   } else {
     // ===================================== epilogue =====================================
     const int q = warp - NUM_GATHER_WARPS;  // == warp % 4: TMEM lane quadrant this warp may read
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int64_t group = blockIdx.x; group < num_groups; group += gridDim.x, ++it) {
       const int buf = it & 1;
-      mbar_wait(smem_u32(tfull_bar + buf), (it >> 1) & 1);
+      const int64_t rem = num_tiles - group * T;
+      const int t_eff = rem < T ? (int)rem : T;
+      mbar_wait(smem_u32(tfull + buf), (it >> 1) & 1);
       tc_fence_after();
-      const int64_t row = tile * BLOCK_M + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.Cout);
-      float* orow = p.out + row * p.out_pitch;
-      int c0 = 0;
-      for (; c0 + 32 <= p.Cout; c0 += 32) {
-        float v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        if (row < p.n_out) {
+      for (int t = 0; t < t_eff; ++t) {
+        const int64_t row = (group * T + t) * BLOCK_M + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + t * p.Cout);
+        float* orow = p.out + row * p.out_pitch;
+        int c0 = 0;
+        for (; c0 + 32 <= p.Cout; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (row < p.n_out) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              *reinterpret_cast<float4*>(orow + c0 + j) = o;
             }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
           }
         }
-      }
-      if (c0 < p.Cout) {  // 16-column tail (Cout % 32 == 16)
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (row < p.n_out) {
+        if (c0 < p.Cout) {  // 16-column tail (Cout % 32 == 16)
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (row < p.n_out) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            for (int j = 0; j < 16; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              *reinterpret_cast<float4*>(orow + c0 + j) = o;
             }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
+      if (lane == 0) mbar_arrive(smem_u32(tempty + buf));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -335,21 +486,32 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int n_op = precision == 3 ? 2 : 1;
-  const int stage_bytes = n_op * (A_TILE_BYTES + Cout * 128);
-  const int fixed = 1024 /*align slack*/ + (2 * MAX_STAGES + 4) * 8 + 16;
-  int stages = (smem_optin - fixed) / stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  PASCO_CHECK_ARG(stages >= 2, "pasco_conv_forward_tc: not enough shared memory for 2 stages (Cout=%d)", Cout);
+  const int a_stage = n_op * A_TILE_BYTES, b_stage = n_op * Cout * 128;
+  int64_t tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
+  int T = 256 / Cout;
+  if (T < 1) T = 1;
+  if (T > 4) T = 4;
+  while (T > 1 && tiles < (int64_t)T * num_sms()) T >>= 1;   // small inputs: spread tiles over more SMs instead
+  const int idx_bytes = IDX_RING * T * BLOCK_M * 4;
+  const int fixed = 1024 /*align slack*/ + idx_bytes + (4 * MAX_STAGES + 4) * 8 + 16;
+  int sb = 2;
+  int sa = (smem_optin - fixed - sb * b_stage) / a_stage;
+  if (sa > 5) {  // room to spare: deepen the weight ring first
+    sb = 3;
+    sa = (smem_optin - fixed - sb * b_stage) / a_stage;
+  }
+  if (sa > MAX_STAGES) sa = MAX_STAGES;
+  PASCO_CHECK_ARG(sa >= 2, "pasco_conv_forward_tc: not enough shared memory (Cout=%d)", Cout);
   ConvParams p;
   p.in = in; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w; p.bias = bias;
   p.in_scale = in_scale; p.in_shift = in_shift; p.out = out;
   p.n_out = n_out; p.out_pitch = Cout;
   p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
-  p.stages = stages; p.tmem_cols = pow2_cols(2 * Cout);
+  p.sa = sa; p.sb = sb; p.tiles_per_group = T; p.tmem_cols = pow2_cols(2 * T * Cout);
   for (int k = 0; k < 32; ++k) p.koff[k] = (k < K) ? (koff_map ? koff_map[k] : k) : 0;
-  const size_t smem = (size_t)stages * stage_bytes + fixed;
-  int64_t tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
-  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  const size_t smem = (size_t)sa * a_stage + (size_t)sb * b_stage + fixed;
+  int64_t groups = (tiles + T - 1) / T;
+  int grid = (int)(groups < num_sms() ? groups : num_sms());
   cudaError_t e;
   if (precision == 3) {
     e = cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
