@@ -31,11 +31,13 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int KBLK = 64;                    // channels per K-block (= one 128-byte swizzle row of bf16)
 constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB
-constexpr int NUM_GATHER_WARPS = 4;
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int MMA_WARP = NUM_GATHER_WARPS + NUM_EPI_WARPS;      // 8
-constexpr int LOAD_WARP = MMA_WARP + 1;                        // 9
-constexpr int NUM_THREADS = (LOAD_WARP + 1) * 32;              // 320
+constexpr int NUM_GATHER_WARPS = 8;                             // 16 tile rows each
+constexpr int NUM_EPI_WARPS = 4;                                // warps 8-11: warp % 4 = TMEM lane quadrant
+constexpr int MMA_WARP = NUM_GATHER_WARPS + NUM_EPI_WARPS;      // 12
+constexpr int LOAD_WARP = MMA_WARP + 1;                        // 13
+constexpr int NUM_THREADS = (LOAD_WARP + 1) * 32;              // 448
+constexpr int ROWS_PER_WARP = BLOCK_M / NUM_GATHER_WARPS;       // 16
+constexpr int LOADS_PER_SLOT = ROWS_PER_WARP / 2;               // 8 float4 per lane per slot
 constexpr int MAX_STAGES = 8;
 
 struct ConvParams {
@@ -118,7 +120,7 @@ struct SlotIt {
   bool valid;
 };
 
-template <int NSPLIT>
+template <int NSPLIT, bool PROLOGUE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -168,15 +170,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     // ===================================== gather producers =====================================
     const int chunk = lane & 15;  // 16-byte fp32 chunk inside the 64-channel block
     const int rsub = lane >> 4;   // which of the 2 rows this half-warp handles per step
-    const bool affine = p.in_scale != nullptr;
+    const bool affine = PROLOGUE && p.in_scale != nullptr;
 
     // async prefetch of the neighbour indices of (group, k) into ring slot gk % IDX_RING: this warp's 32 rows of
     // each of the group's tiles
     auto prefetch_idx = [&](int64_t group, int k, int gk, int t_eff) {
       int* dst = idx_ring + (gk % IDX_RING) * T * BLOCK_M;
-      for (int t = 0; t < t_eff; ++t) {
-        const int64_t row = (group * T + t) * BLOCK_M + warp * 32 + lane;
-        int* d = dst + t * BLOCK_M + warp * 32 + lane;
+      // lanes 0-15 fetch tile t, lanes 16-31 tile t+1: the warp's 16 rows of each
+      for (int t = lane >> 4; t < t_eff; t += 2) {
+        const int64_t row = (group * T + t) * BLOCK_M + warp * ROWS_PER_WARP + (lane & 15);
+        int* d = dst + t * BLOCK_M + warp * ROWS_PER_WARP + (lane & 15);
         if (row < p.n_out) {
           if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
           else *d = (int)row;
@@ -230,56 +233,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
 
-    float4 va[16], vb[16];
+    float4 va[LOADS_PER_SLOT], vb[LOADS_PER_SLOT];
     uint32_t valid_a = 0, valid_b = 0;
 
     // issue the 16 row-segment loads of one slot into registers
-    auto issue = [&](SlotIt& it, float4 (&v)[16], uint32_t& valid) {
+    auto issue = [&](SlotIt& it, float4 (&v)[LOADS_PER_SLOT], uint32_t& valid) {
       if (it.kb == 0 && it.t == 0) {
         // first use of ring entry gk: it was prefetched IDX_RING-1 entries ago; keep the ring primed
         cp_async_wait<IDX_RING - 2>();
         __syncwarp();
         prefetch_ahead(it, IDX_RING - 1);
       }
-      const int* irow = idx_ring + (it.gk % IDX_RING) * T * BLOCK_M + it.t * BLOCK_M + warp * 32;
+      const int* irow = idx_ring + (it.gk % IDX_RING) * T * BLOCK_M + it.t * BLOCK_M + warp * ROWS_PER_WARP;
       const int cbase = it.kb * KBLK + chunk * 4;
       valid = 0;
+      int srcs[LOADS_PER_SLOT];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int src = irow[i * 2 + rsub];
-        if (src >= 0) {
-          v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)src * p.Cin + cbase));
+      for (int i = 0; i < LOADS_PER_SLOT; ++i) srcs[i] = irow[i * 2 + rsub];
+#pragma unroll
+      for (int i = 0; i < LOADS_PER_SLOT; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (srcs[i] >= 0) {
+          v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)srcs[i] * p.Cin + cbase));
           valid |= 1u << i;
-        } else {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
     // convert + store one slot into its A stage and publish it
-    auto store = [&](const SlotIt& it, float4 (&v)[16], uint32_t valid) {
+    auto store = [&](const SlotIt& it, float4 (&v)[LOADS_PER_SLOT], uint32_t valid) {
       mbar_wait(smem_u32(aempty + stage), phase ^ 1);
       uint8_t* dst = a_smem + (size_t)stage * a_stage_bytes;
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (affine) {
+      if (PROLOGUE && affine) {
         const int cbase = it.kb * KBLK + chunk * 4;
         sc = __ldg(reinterpret_cast<const float4*>(p.in_scale + cbase));
         sh = __ldg(reinterpret_cast<const float4*>(p.in_shift + cbase));
       }
+      // byte offset of (row warp*16 + rsub, 16-byte chunk) inside the swizzled tile; row i*2 adds i*256 and flips
+      // the chunk by (i*2 & 7)
+      const uint32_t row_base = (uint32_t)(warp * ROWS_PER_WARP + rsub);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < LOADS_PER_SLOT; ++i) {
         float4 x = v[i];
-        if ((affine || p.in_act) && ((valid >> i) & 1u)) {
+        if (PROLOGUE && ((valid >> i) & 1u)) {
           x.x = act_apply(fmaf(x.x, sc.x, sh.x), p.in_act);
           x.y = act_apply(fmaf(x.y, sc.y, sh.y), p.in_act);
           x.z = act_apply(fmaf(x.z, sc.z, sh.z), p.in_act);
           x.w = act_apply(fmaf(x.w, sc.w, sh.w), p.in_act);
         }
-        const int trow = warp * 32 + i * 2 + rsub;
-        const uint32_t off = (uint32_t)trow * 128u + (uint32_t)(((chunk >> 1) ^ (trow & 7)) << 4) + (uint32_t)((chunk & 1) << 3);
-        uint2 hi, lo;
-        split4(x, hi, lo);
-        *reinterpret_cast<uint2*>(dst + off) = hi;
-        if (NSPLIT == 3) *reinterpret_cast<uint2*>(dst + A_TILE_BYTES + off) = lo;
+        const uint32_t trow = row_base + i * 2;
+        const uint32_t off = trow * 128u + ((((uint32_t)chunk >> 1) ^ (trow & 7u)) << 4) + (((uint32_t)chunk & 1u) << 3);
+        if (NSPLIT == 3) {
+          uint2 hi, lo;
+          split4(x, hi, lo);
+          *reinterpret_cast<uint2*>(dst + off) = hi;
+          *reinterpret_cast<uint2*>(dst + A_TILE_BYTES + off) = lo;
+        } else {
+          *reinterpret_cast<uint2*>(dst + off) = to_bf16x4(x);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -513,13 +524,14 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   int64_t groups = (tiles + T - 1) / T;
   int grid = (int)(groups < num_sms() ? groups : num_sms());
   cudaError_t e;
-  if (precision == 3) {
-    e = cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_conv_tc<3><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_conv_tc<1><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
-  }
+  const bool prologue = in_scale != nullptr || in_act != 0;
+  auto launch = [&](auto kern) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) kern<<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+    return err;
+  };
+  if (precision == 3) e = prologue ? launch(k_conv_tc<3, true>) : launch(k_conv_tc<3, false>);
+  else e = prologue ? launch(k_conv_tc<1, true>) : launch(k_conv_tc<1, false>);
   if (e != cudaSuccess) {
     set_error("pasco_conv_forward_tc: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
     return -1;

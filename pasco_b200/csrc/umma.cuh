@@ -129,14 +129,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// x ≈ hi + lo with hi = bf16(x), lo = bf16(x − hi): 16 mantissa bits in total
+// x ≈ hi + lo with hi = bf16(x), lo = bf16(x − hi): 16 mantissa bits in total.  Packed conversions only
+// (F2FP.BF16.PACK_AB, full-rate ALU) — the scalar F2F path is quarter rate and dominated the gather warps.
 __device__ __forceinline__ void split4(const float4& x, uint2& hi, uint2& lo) {
-  __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z),
-                h3 = __float2bfloat16_rn(x.w);
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lo.x = pack_bf16x2(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
-  lo.y = pack_bf16x2(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+  const uint32_t h01 = pack_bf16x2(x.x, x.y), h23 = pack_bf16x2(x.z, x.w);
+  hi.x = h01;
+  hi.y = h23;
+  const float r0 = x.x - __uint_as_float(h01 << 16), r1 = x.y - __uint_as_float(h01 & 0xffff0000u);
+  const float r2 = x.z - __uint_as_float(h23 << 16), r3 = x.w - __uint_as_float(h23 & 0xffff0000u);
+  lo.x = pack_bf16x2(r0, r1);
+  lo.y = pack_bf16x2(r2, r3);
 }
+__device__ __forceinline__ uint2 to_bf16x4(const float4& x) { return make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w)); }
 
 }  // namespace umma

@@ -16,8 +16,12 @@ using namespace umma;
 
 namespace {
 
-constexpr int NUM_GATHER_WARPS = 4;
-constexpr int NUM_THREADS = 9 * 32;
+constexpr int NUM_GATHER_WARPS = 8;                 // 8 tile rows each
+constexpr int EPI_WARP0 = NUM_GATHER_WARPS;          // warps 8-11: warp % 4 = TMEM lane quadrant
+constexpr int MMA_WARP = EPI_WARP0 + 4;              // 12
+constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;     // 416
+constexpr int WROWS = 64 / NUM_GATHER_WARPS;         // rows of a 64-row tile per gather warp
+constexpr int WLOADS = WROWS / 2;                    // float4 loads per lane per sub-tile
 constexpr int MAX_STAGES = 8;
 constexpr int WG_R = 64;                  // voxel rows per tile (contraction block)
 constexpr int WG_SUB_BYTES = WG_R * 128;  // one [64 rows][64 ch] bf16 tile = 8 KB
@@ -41,43 +45,57 @@ __device__ __forceinline__ float act_apply(float z, int act) {
   return z;
 }
 
-// gather one [WG_R rows][64 ch] tile: lane l<16 (and l+16) of each warp holds the source row of tile row w*16+l
-template <int NSPLIT, bool AFFINE_OK>
-__device__ __forceinline__ void gather_sub(uint8_t* dst_hi, uint8_t* dst_lo, const float* __restrict__ src, int ld,
-                                           int cbase_blk, int idx, int warp, int lane, const float* scale,
-                                           const float* shift, int act) {
+// One [WG_R rows][64 ch] sub-tile is gathered by 8 warps x 8 rows; lanes (l & 7) of a warp hold the source row of
+// tile row w*8 + (l & 7).  Loads and the convert+store are separate so several sub-tiles can be in flight.
+struct SubRegs {
+  float4 v[WLOADS];
+  uint32_t valid;
+};
+
+__device__ __forceinline__ void sub_load(SubRegs& r, const float* __restrict__ src, int ld, int cbase_blk, int idx, int lane) {
   const int chunk = lane & 15, rsub = lane >> 4;
   const int cbase = cbase_blk + chunk * 4;
+  r.valid = 0;
+#pragma unroll
+  for (int i = 0; i < WLOADS; ++i) {
+    const int s = __shfl_sync(0xffffffffu, idx, i * 2 + rsub);
+    r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s >= 0) {
+      r.v[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)s * ld + cbase));
+      r.valid |= 1u << i;
+    }
+  }
+}
+
+template <int NSPLIT, bool AFFINE_OK>
+__device__ __forceinline__ void sub_store(const SubRegs& r, uint8_t* dst_hi, uint8_t* dst_lo, int cbase_blk, int warp, int lane,
+                                          const float* scale, const float* shift, int act) {
+  const int chunk = lane & 15, rsub = lane >> 4;
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool affine = AFFINE_OK && scale != nullptr;
   if (affine) {
-    sc = __ldg(reinterpret_cast<const float4*>(scale + cbase));
-    sh = __ldg(reinterpret_cast<const float4*>(shift + cbase));
-  }
-  float4 v[8];
-  int srcs[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int r = i * 2 + rsub;  // row within this warp's 16 rows
-    srcs[i] = __shfl_sync(0xffffffffu, idx, r);
-    v[i] = srcs[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)srcs[i] * ld + cbase))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc = __ldg(reinterpret_cast<const float4*>(scale + cbase_blk + chunk * 4));
+    sh = __ldg(reinterpret_cast<const float4*>(shift + cbase_blk + chunk * 4));
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 x = v[i];
-    if (AFFINE_OK && (affine || act) && srcs[i] >= 0) {
+  for (int i = 0; i < WLOADS; ++i) {
+    float4 x = r.v[i];
+    if (AFFINE_OK && (affine || act) && ((r.valid >> i) & 1u)) {
       x.x = act_apply(fmaf(x.x, sc.x, sh.x), act);
       x.y = act_apply(fmaf(x.y, sc.y, sh.y), act);
       x.z = act_apply(fmaf(x.z, sc.z, sh.z), act);
       x.w = act_apply(fmaf(x.w, sc.w, sh.w), act);
     }
-    const int trow = warp * 16 + i * 2 + rsub;
-    const uint32_t off = (uint32_t)trow * 128u + (uint32_t)(((chunk >> 1) ^ (trow & 7)) << 4) + (uint32_t)((chunk & 1) << 3);
-    uint2 hi, lo;
-    split4(x, hi, lo);
-    *reinterpret_cast<uint2*>(dst_hi + off) = hi;
-    if (NSPLIT == 3) *reinterpret_cast<uint2*>(dst_lo + off) = lo;
+    const uint32_t trow = (uint32_t)(warp * WROWS + i * 2 + rsub);
+    const uint32_t off = trow * 128u + ((((uint32_t)chunk >> 1) ^ (trow & 7u)) << 4) + (((uint32_t)chunk & 1u) << 3);
+    if (NSPLIT == 3) {
+      uint2 hi, lo;
+      split4(x, hi, lo);
+      *reinterpret_cast<uint2*>(dst_hi + off) = hi;
+      *reinterpret_cast<uint2*>(dst_lo + off) = lo;
+    } else {
+      *reinterpret_cast<uint2*>(dst_hi + off) = to_bf16x4(x);
+    }
   }
 }
 
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
     mbar_init(smem_u32(done_bar), 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -131,37 +149,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
     int git = 0;
     for (int64_t rt = cta_in_pass; rt < num_rt; rt += p.ctas_per_pass, ++git) {
       const int gb = git & 1;
-      const int64_t my_row = rt * WG_R + warp * 16 + (lane & 15);
+      const int64_t my_row = rt * WG_R + warp * WROWS + (lane & (WROWS - 1));
       const bool row_ok = my_row < p.n_out;
       // ---- gout tile (identity rows) ----
       mbar_wait(smem_u32(gempty_bar + gb), ((git >> 1) & 1) ^ 1);
       {
         uint8_t* g = g_smem + (size_t)gb * g_bytes;
         const int gidx = row_ok ? (int)my_row : -1;
-        for (int nb = 0; nb < NB; ++nb)
-          gather_sub<NSPLIT, false>(g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, p.gout, p.Cout,
-                                    nb * 64, gidx, warp, lane, nullptr, nullptr, 0);
+        for (int nb = 0; nb < NB; nb += 2) {
+          SubRegs r0, r1;
+          sub_load(r0, p.gout, p.Cout, nb * 64, gidx, lane);
+          if (nb + 1 < NB) sub_load(r1, p.gout, p.Cout, (nb + 1) * 64, gidx, lane);
+          sub_store<NSPLIT, false>(r0, g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, nb * 64, warp, lane,
+                                   nullptr, nullptr, 0);
+          if (nb + 1 < NB)
+            sub_store<NSPLIT, false>(r1, g + (size_t)(nb + 1) * WG_SUB_BYTES, g + (size_t)(NB + nb + 1) * WG_SUB_BYTES,
+                                     (nb + 1) * 64, warp, lane, nullptr, nullptr, 0);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(gfull_bar + gb));
       }
       // ---- gathered input sub-tiles, two per stage ----
       for (int u = 0; u < nunits; ++u) {
+        SubRegs r[2];
+        int cbs[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // both sub-tiles' loads in flight before the stage is even free
+          const int sub = (unit0 + u) * 2 + h;
+          int idx = -1;
+          cbs[h] = 0;
+          if (sub < p.num_subs) {
+            const int k = sub / CB;
+            cbs[h] = (sub - k * CB) * 64;
+            if (row_ok) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + my_row) : (int)my_row;
+          }
+          sub_load(r[h], p.in, p.Cin, cbs[h], idx, lane);
+        }
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         uint8_t* a = a_smem + (size_t)stage * a_bytes;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int sub = (unit0 + u) * 2 + h;
-          int idx = -1;
-          int cb = 0;
-          if (sub < p.num_subs) {
-            const int k = sub / CB;
-            cb = sub - k * CB;
-            if (row_ok) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + my_row) : (int)my_row;
-          }
-          gather_sub<NSPLIT, true>(a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, p.in, p.Cin, cb * 64,
-                                   idx, warp, lane, p.in_scale, p.in_shift, p.in_act);
-        }
+        for (int h = 0; h < 2; ++h)
+          sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, cbs[h], warp, lane,
+                                  p.in_scale, p.in_shift, p.in_act);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
@@ -171,7 +201,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
       int stage = 0;
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
     }
   } else {
     // epilogue: after the CTA's last MMA, add the partial dW
-    const int q = warp - NUM_GATHER_WARPS;
+    const int q = warp - EPI_WARP0;
     const bool any_work = cta_in_pass < num_rt;
     if (any_work) {
       mbar_wait(smem_u32(done_bar), 0);
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
