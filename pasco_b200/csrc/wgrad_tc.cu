@@ -39,6 +39,15 @@ struct WgradParams {
   int units_per_pass, num_units, num_subs, passes, ctas_per_pass;
 };
 
+constexpr int IDX_RING = 4;
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ float act_apply(float z, int act) {
   if (act == 1) return fmaxf(z, 0.f);
   if (act == 2) return z > 0.f ? z : 0.01f * z;
@@ -144,54 +153,108 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < NUM_GATHER_WARPS) {
+    // Flat slot sequence per row tile:  GS gout slots (two 64-column blocks each), then one slot per unit (two
+    // gathered sub-tiles).  Every slot = 2 x WLOADS float4 loads per lane; the loads of slot s+1 are in flight in
+    // registers while slot s is converted and stored, and the neighbour indices of unit slots arrive through a
+    // cp.async ring IDX_RING-1 slots ahead.
+    const int GS = (NB + 1) / 2;
+    const int slots_per_rt = GS + nunits;
+    int* idx_ring = reinterpret_cast<int*>(tmem_slot + 4);      // [IDX_RING][2][WG_R] ints
+
+    struct It {
+      int64_t rt;
+      int j;       // slot inside the row tile
+      int e;       // running unit-slot counter → index-ring entry
+      int git;     // row tiles done (gout double buffer)
+      bool valid;
+    };
+    auto advance = [&](It& it) {
+      if (it.j >= GS) ++it.e;
+      if (++it.j < slots_per_rt) return;
+      it.j = 0;
+      ++it.git;
+      it.rt += p.ctas_per_pass;
+      it.valid = it.rt < num_rt;
+    };
+    // prefetch the indices of the unit slot `ahead` unit-slots after it (it must point at a unit slot or a gout slot)
+    auto prefetch = [&](int64_t rt, int u, int e) {
+      // lanes 0-7: rows of sub 0, lanes 8-15: rows of sub 1 (this warp's 8 rows)
+      if (rt < num_rt && lane < 16) {
+        const int h = lane >> 3;
+        const int sub = (unit0 + u) * 2 + h;
+        const int64_t row = rt * WG_R + warp * WROWS + (lane & 7);
+        int* d = idx_ring + ((e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & 7);
+        if (sub < p.num_subs && row < p.n_out) {
+          const int k = sub / CB;
+          if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
+          else *d = (int)row;
+        } else {
+          *d = -1;
+        }
+      }
+      cp_async_commit();
+    };
+    auto prefetch_ahead = [&](const It& it, int ahead) {   // entry it.e + ahead
+      int64_t rt = it.rt;
+      int u = (it.j >= GS ? it.j - GS : 0) + ahead;
+      while (u >= nunits) {
+        u -= nunits;
+        rt += p.ctas_per_pass;
+      }
+      prefetch(rt, u, it.e + ahead);
+    };
+
+    SubRegs ra[2], rb[2];
+    auto issue = [&](const It& it, SubRegs (&r)[2]) {
+      const int64_t my_row = it.rt * WG_R + warp * WROWS + (lane & (WROWS - 1));
+      if (it.j < GS) {                                       // gout slot: identity rows
+        const int gidx = my_row < p.n_out ? (int)my_row : -1;
+        const int nb = it.j * 2;
+        sub_load(r[0], p.gout, p.Cout, nb * 64, gidx, lane);
+        if (nb + 1 < NB) sub_load(r[1], p.gout, p.Cout, (nb + 1) * 64, gidx, lane);
+      } else {
+        cp_async_wait<IDX_RING - 2>();
+        __syncwarp();
+        prefetch_ahead(it, IDX_RING - 1);
+        const int u = it.j - GS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int sub = (unit0 + u) * 2 + h;
+          const int cb = sub < p.num_subs ? sub % CB : 0;
+          const int idx = idx_ring[((it.e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & (WROWS - 1))];
+          sub_load(r[h], p.in, p.Cin, cb * 64, idx, lane);
+        }
+      }
+    };
     int stage = 0;
     uint32_t phase = 0;
-    int git = 0;
-    for (int64_t rt = cta_in_pass; rt < num_rt; rt += p.ctas_per_pass, ++git) {
-      const int gb = git & 1;
-      const int64_t my_row = rt * WG_R + warp * WROWS + (lane & (WROWS - 1));
-      const bool row_ok = my_row < p.n_out;
-      // ---- gout tile (identity rows) ----
-      mbar_wait(smem_u32(gempty_bar + gb), ((git >> 1) & 1) ^ 1);
-      {
+    auto store = [&](const It& it, SubRegs (&r)[2]) {
+      if (it.j < GS) {
+        const int gb = it.git & 1;
+        if (it.j == 0) mbar_wait(smem_u32(gempty_bar + gb), ((it.git >> 1) & 1) ^ 1);
         uint8_t* g = g_smem + (size_t)gb * g_bytes;
-        const int gidx = row_ok ? (int)my_row : -1;
-        for (int nb = 0; nb < NB; nb += 2) {
-          SubRegs r0, r1;
-          sub_load(r0, p.gout, p.Cout, nb * 64, gidx, lane);
-          if (nb + 1 < NB) sub_load(r1, p.gout, p.Cout, (nb + 1) * 64, gidx, lane);
-          sub_store<NSPLIT, false>(r0, g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, nb * 64, warp, lane,
-                                   nullptr, nullptr, 0);
-          if (nb + 1 < NB)
-            sub_store<NSPLIT, false>(r1, g + (size_t)(nb + 1) * WG_SUB_BYTES, g + (size_t)(NB + nb + 1) * WG_SUB_BYTES,
-                                     (nb + 1) * 64, warp, lane, nullptr, nullptr, 0);
+        const int nb = it.j * 2;
+        sub_store<NSPLIT, false>(r[0], g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, nb * 64, warp, lane,
+                                 nullptr, nullptr, 0);
+        if (nb + 1 < NB)
+          sub_store<NSPLIT, false>(r[1], g + (size_t)(nb + 1) * WG_SUB_BYTES, g + (size_t)(NB + nb + 1) * WG_SUB_BYTES,
+                                   (nb + 1) * 64, warp, lane, nullptr, nullptr, 0);
+        if (it.j == GS - 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(gfull_bar + gb));
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(gfull_bar + gb));
-      }
-      // ---- gathered input sub-tiles, two per stage ----
-      for (int u = 0; u < nunits; ++u) {
-        SubRegs r[2];
-        int cbs[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {          // both sub-tiles' loads in flight before the stage is even free
-          const int sub = (unit0 + u) * 2 + h;
-          int idx = -1;
-          cbs[h] = 0;
-          if (sub < p.num_subs) {
-            const int k = sub / CB;
-            cbs[h] = (sub - k * CB) * 64;
-            if (row_ok) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + my_row) : (int)my_row;
-          }
-          sub_load(r[h], p.in, p.Cin, cbs[h], idx, lane);
-        }
+      } else {
+        const int u = it.j - GS;
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         uint8_t* a = a_smem + (size_t)stage * a_bytes;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, cbs[h], warp, lane,
+        for (int h = 0; h < 2; ++h) {
+          const int sub = (unit0 + u) * 2 + h;
+          const int cb = sub < p.num_subs ? sub % CB : 0;
+          sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, cb * 64, warp, lane,
                                   p.in_scale, p.in_shift, p.in_act);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
@@ -200,7 +263,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
           phase ^= 1;
         }
       }
+    };
+
+    It ld;
+    ld.rt = cta_in_pass; ld.j = 0; ld.e = 0; ld.git = 0;
+    ld.valid = ld.rt < num_rt;
+    if (ld.valid) {
+      for (int a = 0; a < IDX_RING - 1; ++a) prefetch_ahead(ld, a);
+      It st = ld;
+      issue(ld, ra);
+      advance(ld);
+      while (st.valid) {
+        if (ld.valid) {
+          issue(ld, rb);
+          advance(ld);
+        }
+        store(st, ra);
+        advance(st);
+        if (!st.valid) break;
+        if (ld.valid) {
+          issue(ld, ra);
+          advance(ld);
+        }
+        store(st, rb);
+        advance(st);
+      }
     }
+    cp_async_wait<0>();
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
@@ -300,7 +389,7 @@ extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t*
   const int n_op = precision == 3 ? 2 : 1;
   const int g_bytes = n_op * (Cout / 64) * WG_SUB_BYTES;
   const int a_bytes = n_op * 2 * WG_SUB_BYTES;
-  const int fixed = 1024 + (2 * MAX_STAGES + 6) * 8 + 16;
+  const int fixed = 1024 + (2 * MAX_STAGES + 6) * 8 + 32 + IDX_RING * 2 * WG_R * 4;
   int stages = (smem_optin - fixed - 2 * g_bytes) / a_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   PASCO_CHECK_ARG(stages >= 2, "pasco_conv_wgrad_tc: not enough shared memory");

@@ -380,5 +380,8 @@ def test_unet_slice_forward_backward_matches_oracle(ME, simt):
     worst = max(errs, key=lambda n: errs[n][0])
     print(f"unet slice (simt={simt}): fwd {e:.2e}; worst param-grad rel-L2 {errs[worst][0]:.1e} ({worst}), "
           f"worst max-norm {max(v[1] for v in errs.values()):.1e}")
-    assert errs[worst][0] <= 1e-3, worst
-    assert max(v[1] for v in errs.values()) <= 2e-2
+    # forward on the CUDA-core path (identical ReLU masks): the tensor-core dgrad/wgrad must agree to 1e-3;
+    # forward on the tensor-core path: a couple of flipped masks in this 2.3k-voxel net move gradients by ~1/sqrt(rows*K)
+    tol = 1e-3 if simt in ("all", "fwd") else 2e-2
+    assert errs[worst][0] <= tol, worst
+    assert max(v[1] for v in errs.values()) <= 5 * tol
