@@ -68,6 +68,13 @@ int pasco_kernel_map_probe(const int32_t* out_coords, int64_t n_out, const uint6
                            const int32_t* table_vals, int64_t capacity, int32_t kernel_size, int32_t sx,
                            int32_t sy, int32_t sz, int32_t* nbr, pasco_stream_t s);
 
+/* same for an anisotropic odd box kernel (kx,ky,kz), K = kx*ky*kz offsets x fastest — the dense bottleneck
+ * kernels (3,3,1), (5,5,3), (7,7,5) of pasco/models/layers.py:656-702 run as sparse convs over the full
+ * stride-8 grid.                                                                                  */
+int pasco_kernel_map_box(const int32_t* out_coords, int64_t n_out, const uint64_t* table_keys,
+                         const int32_t* table_vals, int64_t capacity, int32_t kx, int32_t ky, int32_t kz,
+                         int32_t sx, int32_t sy, int32_t sz, int32_t* nbr, pasco_stream_t s);
+
 /* even kernel == stride (k=2 s=2 conv, k=s max-pool): every child has one parent.
  *   parent_of[i] = row of floor(child_i) in the parent table
  *   slot_of[i]   = kernel offset index of the child inside its parent block (x fastest)
@@ -121,7 +128,8 @@ int pasco_dense_occupancy(const float* dense, int32_t B, int32_t C, int64_t cell
 int64_t pasco_conv_packed_bytes(int32_t K, int32_t Cin, int32_t Cout);
 int pasco_conv_pack_weights(const float* W, int32_t K, int32_t Cin, int32_t Cout, int32_t transpose, void* packed,
                             pasco_stream_t s);
-/* koff_map (host int32[K] or NULL): packed weight slice used for table row k (mirrored offsets for dgrad).
+/* koff_map (host int32[K] or NULL): packed weight slice used for table row k; must be the identity
+ * (NULL) or the reversal K-1-k (mirrored offsets of the input gradient).  K <= 1024.
  * bias: float32[Cout] or NULL.  in_scale/in_shift: optional per-input-channel affine applied
  * in the gather prologue (fused BatchNorm), in_act: 0 none, 1 ReLU, 2 LeakyReLU(0.01) after it.
  * stats: optional float64[2*Cout] accumulating column sum / sum of squares of the output.       */

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "pasco_coords_floor": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
     "pasco_coords_generate_k2": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
     "pasco_kernel_map_probe": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
+    "pasco_kernel_map_box": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "pasco_kernel_map_down": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     "pasco_mask_block_counts": (C.c_int, [_p, _i64, _p, _p]),
     "pasco_mask_compact": (C.c_int, [_p, _i64, _p, _p, _p, _p]),

@@ -7,7 +7,7 @@ using namespace pasco;
 
 constexpr int TR = 16;  // output rows per block
 struct KoffMap {
-  int v[64];
+  int v[256];
 };
 
 // W layout: transposed==0 → W[k][ci][co] ; transposed==1 → W[k][co][ci] (used for dgrad: "Cin" here is the
@@ -77,7 +77,7 @@ extern "C" int pasco_conv_forward_simt(const float* in, const int32_t* nbr, int3
                                        int32_t Cout, const float* W, int32_t w_transposed, const int32_t* koff_map,
                                        const float* bias, float* out, pasco_stream_t s) {
   PASCO_CHECK_ARG(Cout <= 512 && Cin <= 2048, "pasco_conv_forward_simt: channel count too large");
-  PASCO_CHECK_ARG(K <= 64, "pasco_conv_forward_simt: K too large");
+  PASCO_CHECK_ARG(K <= 256, "pasco_conv_forward_simt: K too large");
   if (n_out == 0) return 0;
   cudaStream_t st = (cudaStream_t)s;
   KoffMap km;

@@ -52,7 +52,7 @@ struct ConvParams {
   int64_t out_pitch;
   int K, Cin, Cout, in_act;
   int sa, sb, tiles_per_group, tmem_cols;
-  int koff[32];
+  int koff_base, koff_step;   // weight slice of table row k = koff_base + koff_step * k
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(smem_u32(bempty + stage), phase ^ 1);
             mbar_arrive_expect_tx(smem_u32(bfull + stage), bytes);
-            const uint8_t* src = p.wpk + ((int64_t)p.koff[k] * KB + kb) * (int64_t)p.Cout * 256;
+            const uint8_t* src = p.wpk + ((int64_t)(p.koff_base + p.koff_step * k) * KB + kb) * (int64_t)p.Cout * 256;
             if (NSPLIT == 3) {
               bulk_g2s(smem_u32(b_smem + (size_t)stage * b_stage_bytes), src, bytes, smem_u32(bfull + stage));
             } else {
@@ -488,7 +488,7 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_forward_tc: precision must be 1 (bf16) or 3 (bf16x3)");
   PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_tc: Cin (%d) must be a multiple of 64", Cin);
   PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_tc: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
-  PASCO_CHECK_ARG(K >= 1 && K <= 32, "pasco_conv_forward_tc: K (%d) out of range", K);
+  PASCO_CHECK_ARG(K >= 1 && K <= 1024, "pasco_conv_forward_tc: K (%d) out of range", K);
   PASCO_CHECK_ARG(stats == nullptr, "pasco_conv_forward_tc: fused output statistics are not implemented yet");
   PASCO_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)packed_w) & 15) == 0, "pasco_conv_forward_tc: pointers must be 16-byte aligned");
   (void)n_in;
@@ -519,7 +519,16 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   p.n_out = n_out; p.out_pitch = Cout;
   p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
   p.sa = sa; p.sb = sb; p.tiles_per_group = T; p.tmem_cols = pow2_cols(2 * T * Cout);
-  for (int k = 0; k < 32; ++k) p.koff[k] = (k < K) ? (koff_map ? koff_map[k] : k) : 0;
+  p.koff_base = 0; p.koff_step = 1;
+  if (koff_map) {
+    bool ident = true, rev = true;
+    for (int k = 0; k < K; ++k) {
+      ident = ident && koff_map[k] == k;
+      rev = rev && koff_map[k] == K - 1 - k;
+    }
+    PASCO_CHECK_ARG(ident || rev, "pasco_conv_forward_tc: koff_map must be the identity or the reversal");
+    if (!ident) { p.koff_base = K - 1; p.koff_step = -1; }
+  }
   const size_t smem = (size_t)sa * a_stage + (size_t)sb * b_stage + fixed;
   int64_t groups = (tiles + T - 1) / T;
   int grid = (int)(groups < num_sms() ? groups : num_sms());

@@ -185,6 +185,34 @@ extern "C" int pasco_kernel_map_probe(const int32_t* out_coords, int64_t n_out, 
   return 0;
 }
 
+// anisotropic odd box kernel (kx,ky,kz), offsets x fastest — dense bottleneck kernels (3,3,1) (5,5,3) (7,7,5)
+__global__ void k_kernel_map_box(const int4* __restrict__ out_coords, int64_t n, const uint64_t* __restrict__ keys,
+                                 const int32_t* __restrict__ vals, uint32_t mask, int kx, int ky, int kz, int sx, int sy,
+                                 int sz, int32_t* __restrict__ nbr) {
+  const int K = kx * ky * kz;
+  const int64_t total = n * K;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / n);
+    const int64_t o = t - (int64_t)k * n;
+    const int dx = k % kx - kx / 2, dy = (k / kx) % ky - ky / 2, dz = k / (kx * ky) - kz / 2;
+    int4 c = __ldg(out_coords + o);
+    nbr[t] = table_find(keys, vals, mask, pack_key(c.x, c.y + dx * sx, c.z + dy * sy, c.w + dz * sz));
+  }
+}
+
+extern "C" int pasco_kernel_map_box(const int32_t* out_coords, int64_t n_out, const uint64_t* table_keys,
+                                    const int32_t* table_vals, int64_t capacity, int32_t kx, int32_t ky, int32_t kz,
+                                    int32_t sx, int32_t sy, int32_t sz, int32_t* nbr, pasco_stream_t s) {
+  PASCO_CHECK_ARG(kx % 2 == 1 && ky % 2 == 1 && kz % 2 == 1 && kx <= 15 && ky <= 15 && kz <= 15,
+                  "pasco_kernel_map_box: kernel sizes must be odd and <= 15 (got %d,%d,%d)", kx, ky, kz);
+  PASCO_CHECK_ARG(is_pow2(capacity), "pasco_kernel_map_box: capacity must be a power of two");
+  if (n_out == 0) return 0;
+  k_kernel_map_box<<<grid_for(n_out * kx * ky * kz, 256), 256, 0, (cudaStream_t)s>>>(
+      (const int4*)out_coords, n_out, table_keys, table_vals, (uint32_t)(capacity - 1), kx, ky, kz, sx, sy, sz, nbr);
+  PASCO_CHECK_LAUNCH("pasco_kernel_map_box");
+  return 0;
+}
+
 __global__ void k_kernel_map_down(const int4* __restrict__ child, int64_t n, const uint64_t* __restrict__ keys,
                                   const int32_t* __restrict__ vals, uint32_t mask, int ks, int sx, int sy, int sz,
                                   int32_t* __restrict__ parent_of, int32_t* __restrict__ slot_of,

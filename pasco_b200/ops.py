@@ -112,6 +112,16 @@ def kernel_map_probe(out_coords: torch.Tensor, table: HashTable, kernel_size: in
     return nbr
 
 
+def kernel_map_box(out_coords: torch.Tensor, table: HashTable, ksize: Sequence[int], step: Sequence[int]) -> torch.Tensor:
+    """nbr[kx*ky*kz, N_out] for an anisotropic odd box kernel (offsets x fastest)."""
+    n = out_coords.shape[0]
+    K = int(ksize[0]) * int(ksize[1]) * int(ksize[2])
+    nbr = torch.empty(K, n, dtype=torch.int32, device=out_coords.device)
+    call("pasco_kernel_map_box", ptr(out_coords), n, ptr(table.keys), ptr(table.vals), table.capacity,
+         int(ksize[0]), int(ksize[1]), int(ksize[2]), int(step[0]), int(step[1]), int(step[2]), ptr(nbr))
+    return nbr
+
+
 def kernel_map_down(child_coords: torch.Tensor, parent_table: HashTable, n_parent: int, ks: int,
                     child_stride: Sequence[int], want_nbr: bool = True):
     n = child_coords.shape[0]
@@ -305,7 +315,7 @@ class PackedWeights:
 def _tc_ok(c_contract: int, c_out: int, K: int, kind: str = "fwd") -> bool:
     if _SIMT_KINDS is not None and kind in _SIMT_KINDS:
         return False
-    return (not _FORCE_SIMT) and c_contract % 64 == 0 and c_out % 16 == 0 and 16 <= c_out <= 256 and K <= 32
+    return (not _FORCE_SIMT) and c_contract % 64 == 0 and c_out % 16 == 0 and 16 <= c_out <= 256 and K <= 1024
 
 
 def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
