@@ -133,6 +133,7 @@ def run_ours(a):
     from pasco_b200.net3d import PascoNet
     from pasco_b200.losses import total_loss
     from pasco_b200.synthetic import make_scene
+    from pasco_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -147,10 +148,13 @@ def run_ours(a):
 
     torch.manual_seed(0)
     net = PascoNet(n_classes=N_CLASSES, n_infers=1, in_channels=IN_CH, f=64, num_queries=100).to(dev).train()
+    if world > 1:
+        n_sync = parallel.enable_sync_batchnorm(net)     # Trainer(sync_batchnorm=True), scripts/train.py:216
+        log(f"SyncBatchNorm on {n_sync} fused BN layers")
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4, fused=True)
     n_pool = min(a.pool, a.steps + a.warmup)
-    host_scenes = [pin(make_scene(GRID, OCC, 1, IN_CH, N_CLASSES, seed=1000 * rank + i)) for i in range(n_pool)]
+    host_scenes = [pin(make_scene(GRID, OCC, 1, IN_CH, N_CLASSES, seed=sd)) for sd in parallel.scene_seeds(rank, world, n_pool)]
     dev_scenes = [to_device(s, dev) for s in host_scenes]
     torch.cuda.synchronize()
     flat_grad = None
@@ -163,15 +167,7 @@ def run_ours(a):
         loss.backward()
         if world > 1:       # the reference's DDP gradient all-reduce (scripts/train.py:213), one flat NCCL call
             nonlocal flat_grad
-            gs = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
-            flat_grad = torch.cat([g.reshape(-1) for g in gs])
-            dist.all_reduce(flat_grad)
-            flat_grad /= world
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad = flat_grad[off:off + n].view_as(p)
-                off += n
+            flat_grad = parallel.allreduce_gradients(params, bucket=flat_grad)
         torch.nn.utils.clip_grad_norm_(params, 0.5)
         opt.step()
         return loss
