@@ -171,6 +171,17 @@ int pasco_bn_bwd_apply(const float* dy, const float* x, int64_t n, int32_t C, co
                        const float* shift, int32_t act, const float* coef_a, const float* coef_b,
                        const float* coef_c, float* dx, pasco_stream_t s);
 
+/* ---- MaskPLS masked cross-attention (pasco/models/transformer/blocks.py:73-92 with the attention mask of
+ *      transformer_predictor_v2.py:220-289): Q <= 128 queries against all P voxels, H heads of width D <= 64 ------
+ * q [Q, H*D], k / v [P, H*D] float32 (already projected); logits = scale * q.k; mask = bit rows
+ * uint32 [Q, 2*ceil(P/64)] (bit j of word 2t + j/32 set = key 64t + j masked) or NULL; out [Q, H*D] ZEROED by the
+ * caller; lse [H, Q] receives log-sum-exp per row (needed by the backward).  Two streaming passes over K (row
+ * statistics, then output), tcgen05 for both GEMMs, bf16x3 split operands.                                        */
+int64_t pasco_xattn_workspace_bytes(int32_t Q, int64_t P, int32_t H, int32_t D);
+int pasco_xattn_forward(const float* q, const float* k, const float* v, const uint32_t* mask, int32_t Q, int64_t P,
+                        int32_t H, int32_t D, float scale, float* out, float* lse, float* workspace,
+                        int64_t workspace_bytes, pasco_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

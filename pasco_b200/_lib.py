@@ -49,6 +49,8 @@ PROTOTYPES = {
     "pasco_bn_stats": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "pasco_affine_act": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
     "pasco_bn_bwd_reduce": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _i32, _p, _p]),
+    "pasco_xattn_workspace_bytes": (_i64, [_i32, _i64, _i32, _i32]),
+    "pasco_xattn_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, C.c_float, _p, _p, _p, _i64, _p]),
     "pasco_bn_bwd_apply": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _p]),
 }
 

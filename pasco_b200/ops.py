@@ -523,3 +523,61 @@ class BatchNormAct(torch.autograd.Function):
         call("pasco_bn_bwd_apply", ptr(gy), ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ctx.act,
              ptr(ca), ptr(cb), ptr(cc), ptr(gx))
         return gx, ggamma.float(), gbeta.float(), None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# masked cross-attention of a few queries over all voxels (MaskPLS decoder)
+# ----------------------------------------------------------------------------------------------
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """bool [Q,P] (True = masked) → int32 bit rows [Q, 2*ceil(P/64)], keys beyond P masked."""
+    Q, P = mask.shape
+    W = 2 * ((P + 63) // 64)
+    pad = W * 32 - P
+    m = torch.nn.functional.pad(mask, (0, pad), value=True) if pad else mask
+    sh = torch.arange(32, device=mask.device, dtype=torch.int64)
+    words = (m.view(Q, W, 32).to(torch.int64) << sh).sum(-1)
+    return words.to(torch.int32).contiguous()
+
+
+class MaskedCrossAttention(torch.autograd.Function):
+    """out[q] = concat_h softmax_v(scale·q_h·k_h[v] | mask[q,v]) · v_h[v]  — blocks.py:73-92 with the mask of
+    transformer_predictor_v2.py:220-289.  Forward: two streaming tcgen05 passes (xattn.cu); backward: the same
+    algebra as batched library GEMMs that recompute the probabilities from the saved log-sum-exp."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, heads: int):
+        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        Q, HD = q.shape
+        P = k.shape[0]
+        D = HD // heads
+        scale = float(D) ** -0.5
+        bits = pack_mask_bits(mask) if mask is not None else None
+        out = torch.zeros(Q, HD, dtype=torch.float32, device=q.device)
+        lse = torch.empty(heads, Q, dtype=torch.float32, device=q.device)
+        nbytes = _lib.load().pasco_xattn_workspace_bytes(Q, P, heads, D)
+        ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=q.device)
+        call("pasco_xattn_forward", ptr(q), ptr(k), ptr(v), ptr(bits), Q, P, heads, D, C.c_float(scale), ptr(out),
+             ptr(lse), ptr(ws), nbytes)
+        ctx.save_for_backward(q, k, v, mask, out, lse)
+        ctx.heads, ctx.scale = heads, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v, mask, out, lse = ctx.saved_tensors
+        H, scale = ctx.heads, ctx.scale
+        Q, HD = q.shape
+        D = HD // H
+        hv = lambda t: t.view(t.shape[0], H, D).transpose(0, 1)            # noqa: E731  [H, rows, D]
+        qh, kh, vh, oh, gh = hv(q) * scale, hv(k), hv(v), hv(out), hv(go.contiguous())
+        s = torch.bmm(qh, kh.transpose(1, 2)) - lse.unsqueeze(-1)
+        pr = torch.exp(s)
+        if mask is not None:
+            pr = pr.masked_fill(mask.unsqueeze(0), 0.0)
+        dv = torch.bmm(pr.transpose(1, 2), gh)
+        dp = torch.bmm(gh, vh.transpose(1, 2))
+        ds = pr * (dp - (gh * oh).sum(-1, keepdim=True))
+        dq = torch.bmm(ds, kh) * scale
+        dk = torch.bmm(ds.transpose(1, 2), qh)
+        back = lambda t: t.transpose(0, 1).reshape(t.shape[1], HD)          # noqa: E731
+        return back(dq), back(dk), back(dv), None, None
