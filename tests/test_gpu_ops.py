@@ -342,7 +342,7 @@ def test_masked_cross_attention_matches_reference(ME, P, Q, masked):
     e = relerr(yg, yr)
     eg = max(relerr(qg.grad, qr.grad), relerr(kg.grad, kr.grad), relerr(vg.grad, vr.grad))
     print(f"xattn P={P} Q={Q}: fwd {e:.2e} grads {eg:.2e}")
-    assert e <= 1e-4 and eg <= 1e-4
+    assert e <= 1e-4 and eg <= 5e-4      # backward = fp32 library GEMMs against an fp64 reference
 
 
 # ------------------------------------------------------------------------------------------------
