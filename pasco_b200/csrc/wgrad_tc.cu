@@ -8,6 +8,7 @@
 // "sub-tile" s = (offset k, 64-channel block cb); a unit = two consecutive sub-tiles = one M=128 accumulator of
 // Cout TMEM columns; a CTA keeps 512/Cout units resident in TMEM, walks its share of 64-row tiles, and finally
 // adds its partial dW with fp32 reductions (red.global.add).
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -37,6 +38,7 @@ struct WgradParams {
   int K, Cin, Cout, in_act;
   int stages, tmem_cols;
   int units_per_pass, num_units, num_subs, passes, ctas_per_pass;
+  int dbg;   // PASCO_WGRAD_DEBUG: bit0 = skip MMA issue, bit1 = gather nothing (timing experiments only)
 };
 
 constexpr int IDX_RING = 4;
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
     auto issue = [&](const It& it, SubRegs (&r)[2]) {
       const int64_t my_row = it.rt * WG_R + warp * WROWS + (lane & (WROWS - 1));
       if (it.j < GS) {                                       // gout slot: identity rows
-        const int gidx = my_row < p.n_out ? (int)my_row : -1;
+        int gidx = my_row < p.n_out ? (int)my_row : -1;
+        if (p.dbg & 2) gidx = -1;
         const int nb = it.j * 2;
         sub_load(r[0], p.gout, p.Cout, nb * 64, gidx, lane);
         if (nb + 1 < NB) sub_load(r[1], p.gout, p.Cout, (nb + 1) * 64, gidx, lane);
@@ -221,7 +224,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         for (int h = 0; h < 2; ++h) {
           const int sub = (unit0 + u) * 2 + h;
           const int cb = sub < p.num_subs ? sub % CB : 0;
-          const int idx = idx_ring[((it.e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & (WROWS - 1))];
+          int idx = idx_ring[((it.e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & (WROWS - 1))];
+          if (p.dbg & 2) idx = -1;
           sub_load(r[h], p.in, p.Cin, cb * 64, idx, lane);
         }
       }
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
             const uint32_t acc = (git > 0 || j > 0) ? 1u : 0u;
             const uint64_t da_hi = make_desc_sw128(a_hi + j * 2048, WG_SUB_BYTES, 1024);
             const uint64_t db_hi = make_desc_sw128(g_hi + j * 2048, WG_SUB_BYTES, 1024);
+            if (p.dbg & 1) continue;
             mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
             if (NSPLIT == 3) {
               const uint64_t da_lo = make_desc_sw128(a_lo + j * 2048, WG_SUB_BYTES, 1024);
@@ -397,12 +402,17 @@ extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t*
   p.in = in; p.nbr = nbr; p.gout = gout; p.in_scale = in_scale; p.in_shift = in_shift; p.dW = dW;
   p.n_out = n_out; p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
   p.stages = stages;
+  {
+    const char* d = getenv("PASCO_WGRAD_DEBUG");
+    p.dbg = d ? atoi(d) : 0;
+  }
   p.num_subs = K * (Cin / 64);
   p.num_units = (p.num_subs + 1) / 2;
   p.units_per_pass = 512 / Cout;
   if (p.units_per_pass > p.num_units) p.units_per_pass = p.num_units;
   p.tmem_cols = pow2_cols(p.units_per_pass * Cout);
   p.passes = (p.num_units + p.units_per_pass - 1) / p.units_per_pass;
+  p.units_per_pass = (p.num_units + p.passes - 1) / p.passes;   // balance the passes (8+6 → 7+7)
   int64_t num_rt = (n_out + WG_R - 1) / WG_R;
   int cpp = num_sms() / p.passes;
   if (cpp < 1) cpp = 1;
