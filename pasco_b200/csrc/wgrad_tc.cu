@@ -18,9 +18,8 @@ using namespace umma;
 namespace {
 
 constexpr int NUM_GATHER_WARPS = 8;                 // 8 tile rows each
-constexpr int EPI_WARP0 = NUM_GATHER_WARPS;          // warps 8-11: warp % 4 = TMEM lane quadrant
-constexpr int MMA_WARP = EPI_WARP0 + 4;              // 12
-constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;     // 416
+constexpr int MMA_WARP = NUM_GATHER_WARPS;           // 8 (gather warps 0-3 also run the epilogue: TMEM quadrant = warp % 4)
+constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;     // 288
 constexpr int WROWS = 64 / NUM_GATHER_WARPS;         // rows of a 64-row tile per gather warp
 constexpr int WLOADS = WROWS / 2;                    // float4 loads per lane per sub-tile
 constexpr int MAX_STAGES = 8;
@@ -294,6 +293,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
       }
     }
     cp_async_wait<0>();
+    // epilogue (gather warps 0-3, after their last slot): once the CTA's last MMA has retired, add the partial dW
+    if (warp < 4) {
+    const int q = warp;
+    const bool any_work = cta_in_pass < num_rt;
+    if (any_work) {
+      mbar_wait(smem_u32(done_bar), 0);
+      tc_fence_after();
+      const int L = q * 32 + lane;  // accumulator row = channel within the unit
+      for (int u = 0; u < nunits; ++u) {
+        const int sub = (unit0 + u) * 2 + (L >> 6);
+        const bool ok = sub < p.num_subs;
+        const int k = ok ? sub / CB : 0;
+        const int cb = ok ? sub - k * CB : 0;
+        float* drow = p.dW + ((int64_t)k * p.Cin + cb * 64 + (L & 63)) * p.Cout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * p.Cout);
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
+          }
+        }
+      }
+    }
+  }
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
@@ -335,32 +361,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         mma_commit(smem_u32(gempty_bar + gb));
       }
       mma_commit(smem_u32(done_bar));
-    }
-  } else {
-    // epilogue: after the CTA's last MMA, add the partial dW
-    const int q = warp - EPI_WARP0;
-    const bool any_work = cta_in_pass < num_rt;
-    if (any_work) {
-      mbar_wait(smem_u32(done_bar), 0);
-      tc_fence_after();
-      const int L = q * 32 + lane;  // accumulator row = channel within the unit
-      for (int u = 0; u < nunits; ++u) {
-        const int sub = (unit0 + u) * 2 + (L >> 6);
-        const bool ok = sub < p.num_subs;
-        const int k = ok ? sub / CB : 0;
-        const int cb = ok ? sub - k * CB : 0;
-        float* drow = p.dW + ((int64_t)k * p.Cin + cb * 64 + (L & 63)) * p.Cout;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * p.Cout);
-        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
-          if (ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
-          }
-        }
-      }
     }
   }
   tc_fence_before();
