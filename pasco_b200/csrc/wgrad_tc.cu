@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         for (int h = 0; h < 2; ++h) {
           const int sub = (unit0 + u) * 2 + h;
           const int cb = sub < p.num_subs ? sub % CB : 0;
-          sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, cb * 64, warp, lane,
+          if (!(p.dbg & 8)) sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, cb * 64, warp, lane,
                                   p.in_scale, p.in_shift, p.in_act);
         }
         fence_proxy_async_smem();
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
           float v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (ok) {
+          if (ok && !(p.dbg & 4)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
           }
