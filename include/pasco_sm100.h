@@ -132,15 +132,19 @@ int pasco_conv_pack_weights(const float* W, int32_t K, int32_t Cin, int32_t Cout
  * (NULL) or the reversal K-1-k (mirrored offsets of the input gradient).  K <= 1024.
  * bias: float32[Cout] or NULL.  in_scale/in_shift: optional per-input-channel affine applied
  * in the gather prologue (fused BatchNorm), in_act: 0 none, 1 ReLU, 2 LeakyReLU(0.01) after it.
- * stats: optional float64[2*Cout] accumulating column sum / sum of squares of the output.       */
+ * stats: optional float64[2*Cout] accumulating column sum / sum of squares of the output.
+ * in_pitch / out_pitch: row strides in floats (0 = Cin / Cout) so that a column block of a wider matrix can be
+ * read / written in place — dense Linear layers run as K = 1, nbr = NULL convolutions in column chunks <= 256.  */
 int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
                           int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map,
                           const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
-                          double* stats, float* out, int32_t precision, pasco_stream_t s);
+                          double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
+                          pasco_stream_t s);
 /* dW[k] = sum_o in[nbr[k,o],:]^T @ gout[o,:]   (tcgen05, MN-major operands); dW float32 [K,Cin,Cout] zeroed by caller */
 int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out, int32_t Cin,
                         int32_t Cout, const float* gout, const float* in_scale, const float* in_shift,
-                        int32_t in_act, float* dW, int32_t precision, pasco_stream_t s);
+                        int32_t in_act, float* dW, int32_t precision, int64_t in_pitch, int64_t gout_pitch,
+                        pasco_stream_t s);
 
 /* CUDA-core fp32 reference path of the same contraction (any Cin/Cout; validation + odd shapes) */
 int pasco_conv_forward_simt(const float* in, const int32_t* nbr, int32_t K, int64_t n_out, int32_t Cin,

@@ -49,7 +49,8 @@ struct ConvParams {
   const float* in_shift;
   float* out;
   int64_t n_out;
-  int64_t out_pitch;
+  int64_t out_pitch;   // row stride of out (floats)
+  int64_t in_pitch;    // row stride of in (floats)
   int K, Cin, Cout, in_act;
   int sa, sb, tiles_per_group, tmem_cols;
   int koff_base, koff_step;   // weight slice of table row k = koff_base + koff_step * k
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
       for (int i = 0; i < LOADS_PER_SLOT; ++i) {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (srcs[i] >= 0) {
-          v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)srcs[i] * p.Cin + cbase));
+          v[i] = __ldg(reinterpret_cast<const float4*>(p.in + (int64_t)srcs[i] * p.in_pitch + cbase));
           valid |= 1u << i;
         }
       }
@@ -484,7 +485,8 @@ extern "C" int pasco_conv_pack_weights(const float* W, int32_t K, int32_t Cin, i
 extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
                                      int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map,
                                      const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
-                                     double* stats, float* out, int32_t precision, pasco_stream_t s) {
+                                     double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
+                                     pasco_stream_t s) {
   PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_forward_tc: precision must be 1 (bf16) or 3 (bf16x3)");
   PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_tc: Cin (%d) must be a multiple of 64", Cin);
   PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_tc: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
@@ -516,7 +518,10 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   ConvParams p;
   p.in = in; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w; p.bias = bias;
   p.in_scale = in_scale; p.in_shift = in_shift; p.out = out;
-  p.n_out = n_out; p.out_pitch = Cout;
+  p.n_out = n_out;
+  p.out_pitch = out_pitch > 0 ? out_pitch : Cout;
+  p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
+  PASCO_CHECK_ARG(p.out_pitch % 4 == 0 && p.in_pitch % 4 == 0, "pasco_conv_forward_tc: pitches must be multiples of 4 floats");
   p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
   p.sa = sa; p.sb = sb; p.tiles_per_group = T; p.tmem_cols = pow2_cols(2 * T * Cout);
   p.koff_base = 0; p.koff_step = 1;

@@ -34,6 +34,7 @@ struct WgradParams {
   const float* in_shift;
   float* dW;
   int64_t n_out;
+  int64_t in_pitch, gout_pitch;   // row strides (floats)
   int K, Cin, Cout, in_act;
   int stages, tmem_cols;
   int units_per_pass, num_units, num_subs, passes, ctas_per_pass;
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         int gidx = my_row < p.n_out ? (int)my_row : -1;
         if (p.dbg & 2) gidx = -1;
         const int nb = it.j * 2;
-        sub_load(r[0], p.gout, p.Cout, nb * 64, gidx, lane);
-        if (nb + 1 < NB) sub_load(r[1], p.gout, p.Cout, (nb + 1) * 64, gidx, lane);
+        sub_load(r[0], p.gout, (int)p.gout_pitch, nb * 64, gidx, lane);
+        if (nb + 1 < NB) sub_load(r[1], p.gout, (int)p.gout_pitch, (nb + 1) * 64, gidx, lane);
       } else {
         cp_async_wait<IDX_RING - 2>();
         __syncwarp();
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
           const int cb = sub < p.num_subs ? sub % CB : 0;
           int idx = idx_ring[((it.e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & (WROWS - 1))];
           if (p.dbg & 2) idx = -1;
-          sub_load(r[h], p.in, p.Cin, cb * 64, idx, lane);
+          sub_load(r[h], p.in, (int)p.in_pitch, cb * 64, idx, lane);
         }
       }
     };
@@ -382,7 +383,7 @@ int pow2_cols(int c) {
 extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
                                    int32_t Cin, int32_t Cout, const float* gout, const float* in_scale,
                                    const float* in_shift, int32_t in_act, float* dW, int32_t precision,
-                                   pasco_stream_t s) {
+                                   int64_t in_pitch, int64_t gout_pitch, pasco_stream_t s) {
   PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_wgrad_tc: precision must be 1 or 3");
   PASCO_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256,
                   "pasco_conv_wgrad_tc: Cin (%d) and Cout (%d) must be multiples of 64, Cout <= 256", Cin, Cout);
@@ -401,6 +402,8 @@ extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t*
   WgradParams p;
   p.in = in; p.nbr = nbr; p.gout = gout; p.in_scale = in_scale; p.in_shift = in_shift; p.dW = dW;
   p.n_out = n_out; p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
+  p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
+  p.gout_pitch = gout_pitch > 0 ? gout_pitch : Cout;
   p.stages = stages;
   {
     const char* d = getenv("PASCO_WGRAD_DEBUG");

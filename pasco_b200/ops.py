@@ -337,7 +337,7 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
     if use_tc:
         call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
-             ptr(out), _PRECISION)
+             ptr(out), _PRECISION, 0, 0)
     else:
         assert in_scale is None and in_act == 0, "fused prologue needs the tensor-core path"
         if nbr is None:
@@ -364,7 +364,7 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
         ev0.record()
     if _tc_ok(Cin, 64, 1, "wgrad") and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256:
         call("pasco_conv_wgrad_tc", ptr(feats), feats.shape[0], ptr(nbr), K, n_out, Cin, Cout, ptr(gout),
-             ptr(in_scale), ptr(in_shift), in_act, ptr(dW), _PRECISION)
+             ptr(in_scale), ptr(in_shift), in_act, ptr(dW), _PRECISION, 0, 0)
     else:
         assert in_scale is None and in_act == 0
         if nbr is None:
@@ -581,3 +581,71 @@ class MaskedCrossAttention(torch.autograd.Function):
         dk = torch.bmm(ds.transpose(1, 2), qh)
         back = lambda t: t.transpose(0, 1).reshape(t.shape[1], HD)          # noqa: E731
         return back(dq), back(dk), back(dv), None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# dense Linear layers on the tensor-core conv kernel (K = 1, identity rows, column chunks <= 256)
+# ----------------------------------------------------------------------------------------------
+def _data_ptr_at(t: torch.Tensor, col: int) -> int:
+    return t.data_ptr() + 4 * col
+
+
+def _linear_tc_ok(n_rows: int, cin: int, cout: int) -> bool:
+    return (not _FORCE_SIMT) and n_rows >= 4096 and cin % 64 == 0 and cout % 64 == 0
+
+
+def _gemm_rows(x: torch.Tensor, w_nk: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> None:
+    """out[:, :] = x @ w_nkᵀ (+ bias) with w_nk [N, K] row-major (torch Linear layout), N in chunks of <= 256 columns."""
+    n_rows, kdim = x.shape
+    N = w_nk.shape[0]
+    assert x.is_contiguous() and out.is_contiguous() and kdim % 64 == 0 and N % 16 == 0
+    for c0 in range(0, N, 256):
+        cw = min(256, N - c0)
+        wchunk = w_nk[c0:c0 + cw].contiguous()                       # [cw, K]  == ME layout [1, Cin'=cw, Cout'=K]
+        packed = PackedWeights().get(wchunk.view(1, cw, kdim), True)  # B[n][k] = w[n][k]
+        b = bias[c0:c0 + cw].contiguous() if bias is not None else None
+        call("pasco_conv_forward_tc", ptr(x), n_rows, None, 1, n_rows, kdim, cw, ptr(packed), None, ptr(b), None, None, 0,
+             None, C.c_void_p(_data_ptr_at(out, c0)), _PRECISION, 0, N)
+
+
+class LinearTC(torch.autograd.Function):
+    """y = x @ Wᵀ + b for tall x [N, Cin] on the tcgen05 conv kernel (bf16x3 / bf16 like the convolutions) instead of
+    an fp32 CUDA-core library GEMM.  W is [Cout, Cin] (torch Linear layout)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous().float()
+        y = torch.empty(x.shape[0], weight.shape[0], dtype=torch.float32, device=x.device)
+        _gemm_rows(x, weight.detach(), bias.detach() if bias is not None else None, y)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous().float()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _gemm_rows(gy, weight.detach().t().contiguous(), None, gx)          # gx = gy @ W
+        if ctx.needs_input_grad[1]:
+            cout, cin = weight.shape
+            gw = torch.empty(cout, cin, dtype=torch.float32, device=x.device)
+            for c0 in range(0, cin, 256):                                        # dW[:, c0:c0+cw] = gyᵀ @ x[:, c0:c0+cw]
+                cw = min(256, cin - c0)
+                dw = torch.zeros(1, cout, cw, dtype=torch.float32, device=x.device)
+                call("pasco_conv_wgrad_tc", ptr(gy), gy.shape[0], None, 1, gy.shape[0], cout, cw,
+                     C.c_void_p(_data_ptr_at(x, c0)), None, None, 0, ptr(dw), _PRECISION, 0, cin)
+                gw[:, c0:c0 + cw] = dw[0]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear for [N, Cin] inputs: tensor-core path when the shape allows (N >= 4096, Cin, Cout multiples of 64),
+    the fp32 library GEMM otherwise (exactly what MinkowskiEngine does for 1x1 convolutions)."""
+    if x.is_cuda and x.ndim == 2 and _linear_tc_ok(x.shape[0], weight.shape[1], weight.shape[0]):
+        return LinearTC.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)

@@ -310,6 +310,33 @@ def test_fused_batchnorm_act_forward_backward(ME, C, act):
 
 
 # ------------------------------------------------------------------------------------------------
+# dense Linear layers on the tensor-core conv kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,cin,cout,bias", [(5000, 64, 384, True), (6000, 384, 384, True), (4500, 384, 128, False),
+                                              (4100, 128, 64, True)])
+def test_linear_tensor_core_matches_fp64(ME, n, cin, cout, bias):
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(n)
+    x, w = torch.randn(n, cin, generator=g), torch.randn(cout, cin, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g) if bias else None
+    up = torch.randn(n, cout, generator=g)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True) if bias else None
+    (torch.nn.functional.linear(xr, wr, br) * up.double()).sum().backward()
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bg = b.cuda().requires_grad_(True) if bias else None
+    y = ops.linear(xg, wg, bg)
+    assert y.grad_fn.__class__.__name__ == "LinearTCBackward"
+    (y * up.cuda()).sum().backward()
+    e = [relerr(y, torch.nn.functional.linear(xr, wr, br)), relerr(xg.grad, xr.grad), relerr(wg.grad, wr.grad)]
+    if bias:
+        e.append(relerr(bg.grad, br.grad))
+    print(f"linear {n}x{cin}->{cout}: " + " ".join(f"{v:.1e}" for v in e))
+    assert max(e) <= TOL_TIGHT
+
+
+# ------------------------------------------------------------------------------------------------
 # masked cross-attention kernel
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("P,Q,masked", [(3000, 100, True), (64, 100, True), (37, 5, False), (20011, 100, True)])
