@@ -110,7 +110,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int IDX_RING = 4;  // neighbour-index ring depth (entries of T*128 ints, one per (tile group, offset))
+constexpr int IDX_RING = 6;  // neighbour-index ring depth (entries of T*128 ints, one per (tile group, offset))
 
 // position of a gather warp inside the flat slot sequence  group → k → kb → t
 struct SlotIt {

@@ -41,7 +41,7 @@ struct WgradParams {
   int dbg;   // PASCO_WGRAD_DEBUG: bit0 = skip MMA issue, bit1 = gather nothing (timing experiments only)
 };
 
-constexpr int IDX_RING = 4;
+constexpr int IDX_RING = 16;   // unit slots are short: fetch neighbour indices 15 slots ahead (HBM-latency bound otherwise)
 
 __device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
