@@ -148,118 +148,104 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
     mbar_init(smem_u32(done_bar), 1);
     fence_barrier_init();
   }
+  // slot descriptor table: [j][0]=type (0 gout, 1 unit), [1],[2]=column bases of the two sub-tiles (-1 = none),
+  // [3],[4]=kernel offset of the two sub-tiles (-1 = padding)
+  int* idx_ring = reinterpret_cast<int*>(tmem_slot + 4);            // [IDX_RING][2][WG_R]
+  int* desc = idx_ring + IDX_RING * 2 * WG_R;                        // [<=16][8]
+  {
+    const int GSd = (NB + 1) / 2;
+    for (int j = threadIdx.x; j < GSd + nunits; j += NUM_THREADS) {
+      int* dj = desc + j * 8;
+      if (j < GSd) {
+        dj[0] = 0; dj[1] = j * 2 * 64; dj[2] = (j * 2 + 1 < NB) ? (j * 2 + 1) * 64 : -1; dj[3] = -1; dj[4] = -1;
+      } else {
+        dj[0] = 1;
+        for (int h = 0; h < 2; ++h) {
+          const int sub = (unit0 + (j - GSd)) * 2 + h;
+          const bool ok = sub < p.num_subs;
+          dj[1 + h] = ok ? (sub % CB) * 64 : 0;
+          dj[3 + h] = ok ? sub / CB : -1;
+        }
+      }
+    }
+  }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int GS = (NB + 1) / 2;
+  const int spr = GS + nunits;               // slots per row tile
 
   if (warp < NUM_GATHER_WARPS) {
     // Flat slot sequence per row tile:  GS gout slots (two 64-column blocks each), then one slot per unit (two
     // gathered sub-tiles).  Every slot = 2 x WLOADS float4 loads per lane; the loads of slot s+1 are in flight in
-    // registers while slot s is converted and stored, and the neighbour indices of unit slots arrive through a
-    // cp.async ring IDX_RING-1 slots ahead.
-    const int GS = (NB + 1) / 2;
-    const int slots_per_rt = GS + nunits;
-    int* idx_ring = reinterpret_cast<int*>(tmem_slot + 4);      // [IDX_RING][2][WG_R] ints
+    // registers while slot s is converted and stored; neighbour indices arrive through a cp.async ring PF_DIST slots
+    // ahead.  Slot geometry comes from a small descriptor table in shared memory (no divisions in the loop).
+    const int my_r = warp * WROWS + (lane & (WROWS - 1));          // this lane's row inside the 64-row tile
+    const int64_t stride_rt = p.ctas_per_pass;
+    constexpr int PF_DIST = 12;
 
-    struct It {
-      int64_t rt;
-      int j;       // slot inside the row tile
-      int e;       // running unit-slot counter → index-ring entry
-      int git;     // row tiles done (gout double buffer)
-      bool valid;
-    };
-    auto advance = [&](It& it) {
-      if (it.j >= GS) ++it.e;
-      if (++it.j < slots_per_rt) return;
-      it.j = 0;
-      ++it.git;
-      it.rt += p.ctas_per_pass;
-      it.valid = it.rt < num_rt;
-    };
-    // prefetch the indices of the unit slot `ahead` unit-slots after it (it must point at a unit slot or a gout slot)
-    auto prefetch = [&](int64_t rt, int u, int e) {
-      // lanes 0-7: rows of sub 0, lanes 8-15: rows of sub 1 (this warp's 8 rows)
-      if (rt < num_rt && lane < 16) {
+    auto prefetch = [&](int64_t rt, int j, int g) {              // indices of slot (rt, j) → ring entry g
+      if (lane < 16) {
         const int h = lane >> 3;
-        const int sub = (unit0 + u) * 2 + h;
+        const int k = desc[j * 8 + 3 + h];
+        int* d = idx_ring + ((g & (IDX_RING - 1)) * 2 + h) * WG_R + warp * WROWS + (lane & 7);
         const int64_t row = rt * WG_R + warp * WROWS + (lane & 7);
-        int* d = idx_ring + ((e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & 7);
-        if (sub < p.num_subs && row < p.n_out) {
-          const int k = sub / CB;
-          if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
-          else *d = (int)row;
-        } else {
-          *d = -1;
-        }
+        if (k >= 0 && rt < num_rt && row < p.n_out && !(p.dbg & 16)) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
+        else *d = (k >= 0 && rt < num_rt && row < p.n_out) ? (int)row : -1;
       }
       cp_async_commit();
     };
-    auto prefetch_ahead = [&](const It& it, int ahead) {   // entry it.e + ahead
-      int64_t rt = it.rt;
-      int u = (it.j >= GS ? it.j - GS : 0) + ahead;
-      while (u >= nunits) {
-        u -= nunits;
-        rt += p.ctas_per_pass;
-      }
-      prefetch(rt, u, it.e + ahead);
-    };
-
-    SubRegs ra[2], rb[2];
-    auto issue = [&](const It& it, SubRegs (&r)[2]) {
-      const int64_t my_row = it.rt * WG_R + warp * WROWS + (lane & (WROWS - 1));
-      if (it.j < GS) {                                       // gout slot: identity rows
-        int gidx = my_row < p.n_out ? (int)my_row : -1;
+    auto issue = [&](int64_t rt, int j, int g, SubRegs (&r)[2]) {
+      cp_async_wait<PF_DIST - 1>();
+      __syncwarp();
+      const int* dj = desc + j * 8;
+      const int64_t row = rt * WG_R + my_r;
+      if (dj[0] == 0) {                                            // gout slot: identity rows
+        int gidx = row < p.n_out ? (int)row : -1;
         if (p.dbg & 2) gidx = -1;
-        const int nb = it.j * 2;
-        sub_load(r[0], p.gout, (int)p.gout_pitch, nb * 64, gidx, lane);
-        if (nb + 1 < NB) sub_load(r[1], p.gout, (int)p.gout_pitch, (nb + 1) * 64, gidx, lane);
+        sub_load(r[0], p.gout, (int)p.gout_pitch, dj[1], gidx, lane);
+        if (dj[2] >= 0) sub_load(r[1], p.gout, (int)p.gout_pitch, dj[2], gidx, lane);
       } else {
-        cp_async_wait<IDX_RING - 2>();
-        __syncwarp();
-        prefetch_ahead(it, IDX_RING - 1);
-        const int u = it.j - GS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int sub = (unit0 + u) * 2 + h;
-          const int cb = sub < p.num_subs ? sub % CB : 0;
-          int idx = idx_ring[((it.e % IDX_RING) * 2 + h) * WG_R + warp * WROWS + (lane & (WROWS - 1))];
+          int idx = idx_ring[((g & (IDX_RING - 1)) * 2 + h) * WG_R + my_r];
+          if (!p.nbr && idx >= 0) idx = (int)row;
           if (p.dbg & 2) idx = -1;
-          sub_load(r[h], p.in, (int)p.in_pitch, cb * 64, idx, lane);
+          sub_load(r[h], p.in, (int)p.in_pitch, dj[1 + h], idx, lane);
         }
       }
     };
     int stage = 0;
     uint32_t phase = 0;
-    auto store = [&](const It& it, SubRegs (&r)[2]) {
-      if (it.j < GS) {
-        const int gb = it.git & 1;
-        if (it.j == 0) mbar_wait(smem_u32(gempty_bar + gb), ((it.git >> 1) & 1) ^ 1);
+    auto store = [&](int j, int git, SubRegs (&r)[2]) {
+      const int* dj = desc + j * 8;
+      if (dj[0] == 0) {
+        const int gb = git & 1;
+        if (j == 0) mbar_wait(smem_u32(gempty_bar + gb), ((git >> 1) & 1) ^ 1);
         uint8_t* g = g_smem + (size_t)gb * g_bytes;
-        const int nb = it.j * 2;
-        sub_store<NSPLIT, false>(r[0], g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, nb * 64, warp, lane,
+        const int nb = j * 2;
+        sub_store<NSPLIT, false>(r[0], g + (size_t)nb * WG_SUB_BYTES, g + (size_t)(NB + nb) * WG_SUB_BYTES, 0, warp, lane,
                                  nullptr, nullptr, 0);
-        if (nb + 1 < NB)
-          sub_store<NSPLIT, false>(r[1], g + (size_t)(nb + 1) * WG_SUB_BYTES, g + (size_t)(NB + nb + 1) * WG_SUB_BYTES,
-                                   (nb + 1) * 64, warp, lane, nullptr, nullptr, 0);
-        if (it.j == GS - 1) {
+        if (dj[2] >= 0)
+          sub_store<NSPLIT, false>(r[1], g + (size_t)(nb + 1) * WG_SUB_BYTES, g + (size_t)(NB + nb + 1) * WG_SUB_BYTES, 0,
+                                   warp, lane, nullptr, nullptr, 0);
+        if (j == GS - 1) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(gfull_bar + gb));
         }
       } else {
-        const int u = it.j - GS;
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         uint8_t* a = a_smem + (size_t)stage * a_bytes;
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int sub = (unit0 + u) * 2 + h;
-          const int cb = sub < p.num_subs ? sub % CB : 0;
-          if (!(p.dbg & 8)) sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, cb * 64, warp, lane,
-                                  p.in_scale, p.in_shift, p.in_act);
+          for (int h = 0; h < 2; ++h)
+            sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, dj[1 + h], warp, lane,
+                                    p.in_scale, p.in_shift, p.in_act);
         }
-        fence_proxy_async_smem();
+        if (!(p.dbg & 32)) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
         if (++stage == p.stages) {
@@ -269,30 +255,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
       }
     };
 
-    It ld;
-    ld.rt = cta_in_pass; ld.j = 0; ld.e = 0; ld.git = 0;
-    ld.valid = ld.rt < num_rt;
-    if (ld.valid) {
-      for (int a = 0; a < IDX_RING - 1; ++a) prefetch_ahead(ld, a);
-      It st = ld;
-      issue(ld, ra);
-      advance(ld);
-      while (st.valid) {
-        if (ld.valid) {
-          issue(ld, rb);
-          advance(ld);
+    // three cursors over the same slot sequence: prefetch (PF_DIST ahead), load, store
+    int64_t p_rt = cta_in_pass, l_rt = cta_in_pass, s_rt = cta_in_pass;
+    int p_j = 0, l_j = 0, s_j = 0, p_g = 0, l_g = 0, s_git = 0;
+#define WG_ADV(rt, j) do { if (++(j) == spr) { (j) = 0; (rt) += stride_rt; } } while (0)
+    if (l_rt < num_rt) {
+      for (int a = 0; a < PF_DIST; ++a) {
+        prefetch(p_rt, p_j, p_g);
+        ++p_g;
+        WG_ADV(p_rt, p_j);
+      }
+      SubRegs ra[2], rb[2];
+      auto issue_next = [&](SubRegs (&r)[2]) {
+        issue(l_rt, l_j, l_g, r);
+        prefetch(p_rt, p_j, p_g);
+        ++p_g;
+        WG_ADV(p_rt, p_j);
+        ++l_g;
+        WG_ADV(l_rt, l_j);
+      };
+      auto store_next = [&](SubRegs (&r)[2]) {
+        store(s_j, s_git, r);
+        if (++s_j == spr) {
+          s_j = 0;
+          s_rt += stride_rt;
+          ++s_git;
         }
-        store(st, ra);
-        advance(st);
-        if (!st.valid) break;
-        if (ld.valid) {
-          issue(ld, ra);
-          advance(ld);
-        }
-        store(st, rb);
-        advance(st);
+      };
+      issue_next(ra);
+      while (s_rt < num_rt) {
+        if (l_rt < num_rt) issue_next(rb);
+        store_next(ra);
+        if (s_rt >= num_rt) break;
+        if (l_rt < num_rt) issue_next(ra);
+        store_next(rb);
       }
     }
+#undef WG_ADV
     cp_async_wait<0>();
     // epilogue (gather warps 0-3, after their last slot): once the CTA's last MMA has retired, add the partial dW
     if (warp < 4) {
@@ -395,7 +394,7 @@ extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t*
   const int n_op = precision == 3 ? 2 : 1;
   const int g_bytes = n_op * (Cout / 64) * WG_SUB_BYTES;
   const int a_bytes = n_op * 2 * WG_SUB_BYTES;
-  const int fixed = 1024 + (2 * MAX_STAGES + 6) * 8 + 32 + IDX_RING * 2 * WG_R * 4;
+  const int fixed = 1024 + (2 * MAX_STAGES + 6) * 8 + 32 + IDX_RING * 2 * WG_R * 4 + 16 * 8 * 4;
   int stages = (smem_optin - fixed - 2 * g_bytes) / a_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   PASCO_CHECK_ARG(stages >= 2, "pasco_conv_wgrad_tc: not enough shared memory");

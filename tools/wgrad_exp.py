@@ -1,5 +1,5 @@
 import os, sys, subprocess
-for dbg in ("0", "3", "7", "15"):
+for dbg in ("0", "3", "31"):
     env = dict(os.environ, PASCO_WGRAD_DEBUG=dbg)
     r = subprocess.run([sys.executable, "tools/conv_microbench.py", "--occ", "0.5", "--channels", "64", "--out", "/tmp/x.jsonl"],
                        env=env, capture_output=True, text=True)
