@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         const int k = desc[j * 8 + 3 + h];
         int* d = idx_ring + ((g & (IDX_RING - 1)) * 2 + h) * WG_R + warp * WROWS + (lane & 7);
         const int64_t row = rt * WG_R + warp * WROWS + (lane & 7);
-        if (k >= 0 && rt < num_rt && row < p.n_out && !(p.dbg & 16)) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
+        if (p.nbr && k >= 0 && rt < num_rt && row < p.n_out && !(p.dbg & 16)) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
         else *d = (k >= 0 && rt < num_rt && row < p.n_out) ? (int)row : -1;
       }
       cp_async_commit();
