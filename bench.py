@@ -55,6 +55,24 @@ def _peaks():
     return 6650.0, 1400.0, "fallback"
 
 
+def _ncu_traffic(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture of the same layer shape (profiles/r01_ncu_conv_v4.json: N=1.05 M rows, C=64, bf16x3); None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_conv_v4.json")))
+        want = "k_wgrad_tc" if kind == "wgrad" else "k_conv_tc"
+        for k in d["kernels"]:
+            if want in k["kernel"]:
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = k[key].split()
+                    tot += float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[u]
+                return {"bytes_per_launch": tot, "source": "profiles/r01_ncu_conv_v4.json (C=64, N=1.05M rows)"}
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -208,6 +226,7 @@ def run_ours(a):
     ms, _ = timed(a.steps, from_host=False)
     launches = ops.CALLS - calls0
     prof, ops.PROFILE = ops.PROFILE, None
+    ops.PAIR_COUNTS.clear()
     log(f"device-resident region: {ms / a.steps:.1f} ms/step")
     ms_e2e, _ = timed(a.steps, from_host=True)
     log(f"e2e region: {ms_e2e / a.steps:.1f} ms/step")
@@ -218,7 +237,7 @@ def run_ours(a):
     for kind, e_a, e_b, m in prof:
         key = (kind, m["n_out"] // 50000, m["K"], m["Cin"], m["Cout"])
         g = groups.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "kind": kind, "meta": m})
-        pairs = float((m["nbr"] >= 0).sum().item()) if m["nbr"] is not None else float(m["n_out"])
+        pairs = float(m["pairs"].item()) if m.get("pairs") is not None else float(m["n_out"]) * (m["K"] if m["K"] > 1 else 1)
         g["ms"] += e_a.elapsed_time(e_b)
         g["n"] += 1
         g["flops"] += 2.0 * pairs * m["Cin"] * m["Cout"]
@@ -234,7 +253,7 @@ def run_ours(a):
         m = top["meta"]
         roof = {"kernel": f"k_conv_tc<{m['precision']}> {top['kind']} K={m['K']} {m['Cin']}->{m['Cout']} n_out~{m['n_out']}",
                 "bound": "tensor", "achieved": round(ach_tf, 2), "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": round(ach_tf / tf_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach_tf / tf_peak, 4), "traffic": _ncu_traffic(top["kind"]), "peak_source": peak_src,
                 "launch_ms": round(per_launch_ms, 4), "launches": top["n"],
                 "algorithmic": "flops = 2*pairs*Cin*Cout per launch (useful MACs; bf16x3 issues 3x that on the tensor pipe)",
                 "hbm_achieved_GBs": round(ach_gb, 1), "hbm_frac": round(ach_gb / hbm_peak, 4),

@@ -23,6 +23,7 @@ _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
 _SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} forced onto the CUDA-core path
 PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
+PAIR_COUNTS = {}        # nbr.data_ptr() → 0-dim device tensor with the number of valid pairs (profiling only)
 CALLS = 0               # number of C-ABI compute calls (each launches >= 1 kernel of ours)
 
 
@@ -282,6 +283,8 @@ class KernelMap:
 
     def __init__(self, nbr, n_in, n_out, nbr_t=None, koff_t=None, build_t=None):
         self.nbr, self.n_in, self.n_out = nbr, n_in, n_out
+        if PROFILE is not None:
+            PAIR_COUNTS[nbr.data_ptr()] = (nbr >= 0).sum()
         self._nbr_t, self._koff_t, self._build_t = nbr_t, koff_t, build_t
         self.K = nbr.shape[0]
 
@@ -348,7 +351,8 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
         prof.append(("dgrad" if transpose_w else "fwd", ev0, ev1,
-                     dict(n_in=feats.shape[0], n_out=n_out, K=kk, Cin=c_contract, Cout=c_out, nbr=nbr,
+                     dict(n_in=feats.shape[0], n_out=n_out, K=kk, Cin=c_contract, Cout=c_out,
+                          pairs=PAIR_COUNTS.get(nbr.data_ptr()) if nbr is not None else None,
                           tc=use_tc, precision=_PRECISION)))
     return out
 
@@ -373,7 +377,8 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
-        prof.append(("wgrad", ev0, ev1, dict(n_in=feats.shape[0], n_out=n_out, K=K, Cin=Cin, Cout=Cout, nbr=nbr,
+        prof.append(("wgrad", ev0, ev1, dict(n_in=feats.shape[0], n_out=n_out, K=K, Cin=Cin, Cout=Cout,
+                                             pairs=PAIR_COUNTS.get(nbr.data_ptr()) if nbr is not None else None,
                                              tc=True, precision=_PRECISION)))
     return dW
 
