@@ -185,6 +185,11 @@ int64_t pasco_xattn_workspace_bytes(int32_t Q, int64_t P, int32_t H, int32_t D);
 int pasco_xattn_forward(const float* q, const float* k, const float* v, const uint32_t* mask, int32_t Q, int64_t P,
                         int32_t H, int32_t D, float scale, float* out, float* lse, float* workspace,
                         int64_t workspace_bytes, pasco_stream_t s);
+/* backward of the above: recomputes the probabilities from lse; dq [Q, H*D] ZEROED by the caller (fp32 red.add),
+ * dk / dv [P, H*D] are fully overwritten (every row written exactly once, no atomics).                            */
+int pasco_xattn_backward(const float* q, const float* k, const float* v, const uint32_t* mask, const float* lse,
+                         const float* out, const float* dout, int32_t Q, int64_t P, int32_t H, int32_t D, float scale,
+                         float* dq, float* dk, float* dv, pasco_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -546,8 +546,8 @@ def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
 
 class MaskedCrossAttention(torch.autograd.Function):
     """out[q] = concat_h softmax_v(scale·q_h·k_h[v] | mask[q,v]) · v_h[v]  — blocks.py:73-92 with the mask of
-    transformer_predictor_v2.py:220-289.  Forward: two streaming tcgen05 passes (xattn.cu); backward: the same
-    algebra as batched library GEMMs that recompute the probabilities from the saved log-sum-exp."""
+    transformer_predictor_v2.py:220-289.  Forward: two streaming tcgen05 passes; backward: one streaming pass with
+    five tcgen05 GEMM groups per 64-key tile that recomputes the probabilities from the saved log-sum-exp (xattn.cu)."""
 
     @staticmethod
     def forward(ctx, q, k, v, mask, heads: int):
@@ -563,29 +563,22 @@ class MaskedCrossAttention(torch.autograd.Function):
         ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=q.device)
         call("pasco_xattn_forward", ptr(q), ptr(k), ptr(v), ptr(bits), Q, P, heads, D, C.c_float(scale), ptr(out),
              ptr(lse), ptr(ws), nbytes)
-        ctx.save_for_backward(q, k, v, mask, out, lse)
+        ctx.save_for_backward(q, k, v, bits, out, lse)
         ctx.heads, ctx.scale = heads, scale
         return out
 
     @staticmethod
     def backward(ctx, go):
-        q, k, v, mask, out, lse = ctx.saved_tensors
+        q, k, v, bits, out, lse = ctx.saved_tensors
         H, scale = ctx.heads, ctx.scale
         Q, HD = q.shape
-        D = HD // H
-        hv = lambda t: t.view(t.shape[0], H, D).transpose(0, 1)            # noqa: E731  [H, rows, D]
-        qh, kh, vh, oh, gh = hv(q) * scale, hv(k), hv(v), hv(out), hv(go.contiguous())
-        s = torch.bmm(qh, kh.transpose(1, 2)) - lse.unsqueeze(-1)
-        pr = torch.exp(s)
-        if mask is not None:
-            pr = pr.masked_fill(mask.unsqueeze(0), 0.0)
-        dv = torch.bmm(pr.transpose(1, 2), gh)
-        dp = torch.bmm(gh, vh.transpose(1, 2))
-        ds = pr * (dp - (gh * oh).sum(-1, keepdim=True))
-        dq = torch.bmm(ds, kh) * scale
-        dk = torch.bmm(ds.transpose(1, 2), qh)
-        back = lambda t: t.transpose(0, 1).reshape(t.shape[1], HD)          # noqa: E731
-        return back(dq), back(dk), back(dv), None, None
+        P = k.shape[0]
+        go = go.contiguous().float()
+        dq = torch.zeros_like(q)
+        dk, dv = torch.empty_like(k), torch.empty_like(v)
+        call("pasco_xattn_backward", ptr(q), ptr(k), ptr(v), ptr(bits), ptr(lse), ptr(out), ptr(go), Q, P, H, HD // H,
+             C.c_float(scale), ptr(dq), ptr(dk), ptr(dv))
+        return dq, dk, dv, None, None
 
 
 # ----------------------------------------------------------------------------------------------
