@@ -37,6 +37,18 @@ def test_state_dict_names_and_shapes_match_the_reference():
     assert sum(int(np.prod(s)) for s in ref.values()) > 100e6
 
 
+@pytest.mark.parametrize("variant,M,heavy", [("m2_light", 2, False), ("m1_heavy", 1, True), ("m3_light", 3, False)])
+def test_state_dict_matches_reference_for_mimo_and_heavy_decoder(variant, M, heavy):
+    """Checkpoint compatibility of the other shipped configurations: MIMO M=2/3 and heavy_decoder=True
+    (manifests dumped from the reference's own Net.state_dict(), tests/golden/manifests_variants.json)."""
+    from pasco_b200.net3d import PascoNet
+    ref = json.load(open(os.path.join(HERE, "golden", "manifests_variants.json")))[variant]
+    net = PascoNet(n_classes=20, n_infers=M, in_channels=283, f=64, num_queries=100, heavy_decoder=heavy)
+    mine = {k: list(v.shape) for k, v in net.reference_state_dict().items()}
+    assert sorted(mine) == sorted(ref), (sorted(set(ref) - set(mine))[:5], sorted(set(mine) - set(ref))[:5])
+    assert all(mine[k] == ref[k] for k in ref)
+
+
 def test_reference_state_dict_round_trip():
     net = _net()
     sd = fill_state_dict(net.reference_state_dict())
@@ -99,3 +111,38 @@ def test_full_forward_matches_reference_golden():
                    / np.abs(gold[f"aux{i}_query_logits"]).max())
         assert ea <= 1e-3, f"aux {i} query logits error {ea:.3e}"
     print("golden parity:", report, "query", eq)
+
+
+@pytest.mark.gpu
+def test_mimo_m2_forward_matches_reference_golden():
+    """MIMO wrapper, M=2 (two scenes channel-concatenated through one trunk, per-subnet heads and transformer
+    passes incl. the reference's zero-padding of the shorter subnet): golden from the unmodified reference."""
+    from pasco_b200 import ops
+    from pasco_b200.net3d import PascoNet
+    from pasco_b200.synthetic import make_scene
+    ops.set_precision("fp32")
+    man = json.load(open(os.path.join(HERE, "golden", "net_cfg1_m2_manifest.json")))
+    gold = np.load(os.path.join(HERE, "golden", "net_cfg1_m2.npz"))
+    torch.manual_seed(0)
+    net = PascoNet(n_classes=20, n_infers=2, in_channels=283, f=64, num_queries=100)
+    net.load_reference_state_dict(fill_state_dict(net.reference_state_dict()))
+    net.cuda().train()
+    b = make_scene(man["grid"], man["occ"], 2, seed=man["seed"])
+    dev = torch.device("cuda")
+    with torch.no_grad():
+        out = net([f.to(dev) for f in b["in_feats"]], [c.to(dev) for c in b["in_coords"]],
+                  b["global_min_Cs"], b["global_max_Cs"], b["min_Cs"], b["max_Cs"])
+    step, report = man["row_step"], {}
+    for m in range(2):
+        for s in (4, 2, 1):
+            lg = out["sem_logits_at_scales"][s][m]
+            report[f"sem{s}_m{m}"] = _compare(f"sem{s}_m{m}", lg.C, lg.F, gold[f"sem{s}_m{m}_C"], gold[f"sem{s}_m{m}_F"], step)
+        p = out["panop_predictions"][m]
+        report[f"vox_m{m}"] = _compare(f"vox_m{m}", p["voxel_logits"].C, p["voxel_logits"].F, gold[f"vox_m{m}_C"],
+                                       gold[f"vox_m{m}_F"], step)
+        q = p["query_logits"][0].cpu()
+        eq = float((q.double() - torch.as_tensor(gold[f"query_logits_m{m}"]).double()).abs().max()
+                   / np.abs(gold[f"query_logits_m{m}"]).max())
+        assert eq <= 1e-3, f"subnet {m} query logits error {eq:.3e}"
+        report[f"query_m{m}"] = eq
+    print("MIMO M=2 golden parity:", report)
