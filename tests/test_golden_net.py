@@ -64,7 +64,7 @@ def _keys(C):
     return ((c[:, 0] + 32768) << 48) | ((c[:, 1] + 32768) << 32) | ((c[:, 2] + 32768) << 16) | (c[:, 3] + 32768)
 
 
-def _compare(name, got_C, got_F, gold_C, gold_F_sub, step, tol=1e-3):
+def _compare(name, got_C, got_F, gold_C, gold_F_sub, step, tol=1e-3, check=True):
     gk, rk = _keys(got_C.cpu().numpy()), _keys(gold_C)
     order = torch.argsort(gk)
     gk, gF = gk[order], got_F.detach().cpu()[order]
@@ -77,7 +77,7 @@ def _compare(name, got_C, got_F, gold_C, gold_F_sub, step, tol=1e-3):
     ref = torch.as_tensor(gold_F_sub)[hit]
     got = gF[pos[hit]]
     err = float((got.double() - ref.double()).abs().max() / ref.double().abs().max())
-    assert err <= tol, f"{name}: feature error {err:.3e} > {tol}"
+    assert (not check) or err <= tol, f"{name}: feature error {err:.3e} > {tol}"
     return sym, err
 
 
@@ -136,13 +136,17 @@ def test_mimo_m2_forward_matches_reference_golden():
     for m in range(2):
         for s in (4, 2, 1):
             lg = out["sem_logits_at_scales"][s][m]
-            report[f"sem{s}_m{m}"] = _compare(f"sem{s}_m{m}", lg.C, lg.F, gold[f"sem{s}_m{m}_C"], gold[f"sem{s}_m{m}_F"], step)
+            report[f"sem{s}_m{m}"] = _compare(f"sem{s}_m{m}", lg.C, lg.F, gold[f"sem{s}_m{m}_C"], gold[f"sem{s}_m{m}_F"], step, check=False)
         p = out["panop_predictions"][m]
         report[f"vox_m{m}"] = _compare(f"vox_m{m}", p["voxel_logits"].C, p["voxel_logits"].F, gold[f"vox_m{m}_C"],
-                                       gold[f"vox_m{m}_F"], step)
+                                       gold[f"vox_m{m}_F"], step, check=False)
         q = p["query_logits"][0].cpu()
         eq = float((q.double() - torch.as_tensor(gold[f"query_logits_m{m}"]).double()).abs().max()
                    / np.abs(gold[f"query_logits_m{m}"]).max())
-        assert eq <= 1e-3, f"subnet {m} query logits error {eq:.3e}"
         report[f"query_m{m}"] = eq
+        for i, aux in enumerate(p["aux_outputs"]):
+            report[f"aux{i}_m{m}"] = float((aux["query_logits"][0].cpu().double() - torch.as_tensor(gold[f"aux{i}_query_logits_m{m}"]).double()).abs().max()
+                                           / np.abs(gold[f"aux{i}_query_logits_m{m}"]).max())
     print("MIMO M=2 golden parity:", report)
+    worst = max(v[1] if isinstance(v, tuple) else v for v in report.values())
+    assert worst <= 1e-3, report
