@@ -22,6 +22,7 @@ def call(name, *args):
 _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
 _SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} forced onto the CUDA-core path
+_USE_PLANES = True      # forward / input-gradient convs gather pre-split bf16 planes with cp.async (conv_planes.cu)
 PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
 PAIR_COUNTS = {}        # nbr.data_ptr() → 0-dim device tensor with the number of valid pairs (profiling only)
 CALLS = 0               # number of C-ABI compute calls (each launches >= 1 kernel of ours)
@@ -315,6 +316,20 @@ class PackedWeights:
         return buf
 
 
+def use_planes(flag: bool) -> None:
+    global _USE_PLANES
+    _USE_PLANES = bool(flag)
+
+
+def split_planes(x: torch.Tensor, scale=None, shift=None, act: int = 0):
+    """x fp32 [N,C] → (hi, lo) bf16 planes of act(x*scale+shift); lo is None in bf16 mode."""
+    n, c = x.shape
+    hi = torch.empty(n, c, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(n, c, dtype=torch.bfloat16, device=x.device) if _PRECISION == 3 else None
+    call("pasco_split_planes", ptr(x), n, c, 0, ptr(scale), ptr(shift), act, ptr(hi), ptr(lo))
+    return hi, lo
+
+
 def _tc_ok(c_contract: int, c_out: int, K: int, kind: str = "fwd") -> bool:
     if _SIMT_KINDS is not None and kind in _SIMT_KINDS:
         return False
@@ -337,7 +352,11 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
     use_tc = _tc_ok(c_contract, c_out, kk, "dgrad" if transpose_w else "fwd")
-    if use_tc:
+    if use_tc and _USE_PLANES:
+        hi, lo = split_planes(feats, in_scale, in_shift, in_act)
+        call("pasco_conv_forward_planes", ptr(hi), ptr(lo), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
+             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(out), _PRECISION, 0)
+    elif use_tc:
         call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
              ptr(out), _PRECISION, 0, 0)

@@ -225,6 +225,19 @@ def test_conv_cuda_core_path(ME, kind, cin, cout):
         ops.force_simt(False)
 
 
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 256, 256), ("down", 64, 128), ("up", 128, 64)])
+def test_conv_register_gather_path(ME, kind, cin, cout):
+    """The fp32-gather kernel (conv_tc.cu, used when a BatchNorm prologue is fused) against the oracle; the default
+    forward path in every other test is the pre-split-plane / cp.async kernel (conv_planes.cu)."""
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    ops.use_planes(False)
+    try:
+        _run_conv_case(ME, kind, cin, cout, TOL_TIGHT)
+    finally:
+        ops.use_planes(True)
+
+
 def test_conv_many_tiles_per_cta(ME):
     """~59k voxels: every persistent CTA walks several 128-row tiles (and several 64-row wgrad tiles
     accumulating in TMEM), unlike the small cases above."""
