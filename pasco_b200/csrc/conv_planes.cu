@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
     // The input arrives pre-split into bf16 planes (hi, lo) [N_in, Cin], so a tile row is a pure 128-byte copy per
     // plane and 64-channel block: 16-byte cp.async (LDGSTS) straight into the swizzled UMMA tile, zero-filled
     // (src-size 0) where the neighbour is missing.  No registers, no conversion: DEPTH slots are in flight per warp.
-    constexpr int DEPTH = 3;
+    constexpr int DEPTH = 3;                                   // slots in flight per warp (bounded by the ring: sa - 1)
+    const int depth = p.sa - 1 < DEPTH ? p.sa - 1 : DEPTH;
     const int crow = lane >> 3;      // 4 rows per instruction
     const int cchunk = lane & 7;     // 16-byte chunk of the 128-byte row segment
     const int PE = (DEPTH + 1 + T * KB - 1) / (T * KB) + 1;   // index-ring prefetch distance in (group,k) entries
@@ -223,8 +224,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
             }
           }
         }
-        if (in_flight > DEPTH) {
-          cp_async_wait<DEPTH>();
+        if (in_flight > depth) {
+          if (depth >= 3) cp_async_wait<3>();
+          else if (depth == 2) cp_async_wait<2>();
+          else if (depth == 1) cp_async_wait<1>();
+          else cp_async_wait<0>();
           publish();
         }
       }

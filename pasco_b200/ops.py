@@ -22,7 +22,8 @@ def call(name, *args):
 _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
 _SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} forced onto the CUDA-core path
-_USE_PLANES = True      # forward / input-gradient convs gather pre-split bf16 planes with cp.async (conv_planes.cu)
+_USE_PLANES = False     # optional: forward / input-gradient convs gather pre-split bf16 planes with cp.async
+                        # (conv_planes.cu; measured 1.16 vs 1.38 ms at C=64 incl. the split pass, slower at C>=128)
 PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
 PAIR_COUNTS = {}        # nbr.data_ptr() → 0-dim device tensor with the number of valid pairs (profiling only)
 CALLS = 0               # number of C-ABI compute calls (each launches >= 1 kernel of ours)

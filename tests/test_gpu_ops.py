@@ -226,16 +226,15 @@ def test_conv_cuda_core_path(ME, kind, cin, cout):
 
 
 @pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 256, 256), ("down", 64, 128), ("up", 128, 64)])
-def test_conv_register_gather_path(ME, kind, cin, cout):
-    """The fp32-gather kernel (conv_tc.cu, used when a BatchNorm prologue is fused) against the oracle; the default
-    forward path in every other test is the pre-split-plane / cp.async kernel (conv_planes.cu)."""
+def test_conv_presplit_plane_path(ME, kind, cin, cout):
+    """Optional producer variant (conv_planes.cu): activations pre-split into bf16 planes, cp.async gather."""
     from pasco_b200 import ops
     ops.set_precision("fp32")
-    ops.use_planes(False)
+    ops.use_planes(True)
     try:
         _run_conv_case(ME, kind, cin, cout, TOL_TIGHT)
     finally:
-        ops.use_planes(True)
+        ops.use_planes(False)
 
 
 def test_conv_many_tiles_per_cta(ME):

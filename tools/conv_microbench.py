@@ -73,17 +73,17 @@ def main():
             pk = ops.PackedWeights()
             for prec in ("fp32", "bf16"):
                 ops.set_precision(prec)
-                ops.use_planes(False)
-                fwd_reg = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk), flush=flush)
                 ops.use_planes(True)
                 split = timed(lambda: ops.split_planes(F), flush=flush)
+                fwd_planes = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk), flush=flush)
+                ops.use_planes(False)
                 fwd = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk), flush=flush)
                 dgr = timed(lambda: ops.conv_apply(G, W, nbr, N, True, [26 - k for k in range(27)], packs=pk), flush=flush)
                 wgr = timed(lambda: ops.conv_wgrad(F, G, nbr, 27, ch, ch), flush=flush)
                 flops = 2.0 * pairs * ch * ch
                 dense_flops = 2.0 * N * 27 * ch * ch
                 bytes_min = 4.0 * (2 * N * ch) + 4.0 * 27 * ch * ch + 4.0 * 27 * N
-                emit(kind="conv3", occ=occ, N=N, C=ch, precision=prec, fwd_ms=fwd, fwd_regpath_ms=fwd_reg, split_ms=split, dgrad_ms=dgr, wgrad_ms=wgr,
+                emit(kind="conv3", occ=occ, N=N, C=ch, precision=prec, fwd_ms=fwd, fwd_planes_ms=fwd_planes, split_ms=split, dgrad_ms=dgr, wgrad_ms=wgr,
                      fwd_useful_TFLOPs=flops / fwd / 1e9, fwd_issued_TFLOPs=dense_flops / fwd / 1e9 * (3 if prec == "fp32" else 1),
                      fwd_alg_GBs=bytes_min / fwd / 1e6, wgrad_useful_TFLOPs=flops / wgr / 1e9)
             ops.set_precision("fp32")
