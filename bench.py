@@ -256,6 +256,8 @@ def run_ours(a):
                 "frac": round(ach_tf / tf_peak, 4), "traffic": _ncu_traffic(top["kind"]), "peak_source": peak_src,
                 "launch_ms": round(per_launch_ms, 4), "launches": top["n"],
                 "algorithmic": "flops = 2*pairs*Cin*Cout per launch (useful MACs; bf16x3 issues 3x that on the tensor pipe)",
+                "tensor_issued_TFLOPs": round(ach_tf * (3 if m["precision"] == 3 else 1), 2),
+                "tensor_issued_frac": round(ach_tf * (3 if m["precision"] == 3 else 1) / tf_peak, 4),
                 "hbm_achieved_GBs": round(ach_gb, 1), "hbm_frac": round(ach_gb / hbm_peak, 4),
                 "share_of_step": round(top["ms"] / ms, 3), "all_conv_share_of_step": round(conv_ms / ms, 3)}
 
