@@ -243,6 +243,10 @@ def run_ours(a):
         g["flops"] += 2.0 * pairs * m["Cin"] * m["Cout"]
         g["bytes"] += 4.0 * (m["n_in"] * m["Cin"] + m["n_out"] * m["Cout"]) + 4.0 * m["K"] * m["Cin"] * m["Cout"] + 8.0 * pairs
     conv_ms = sum(g["ms"] for g in groups.values())
+    if rank == 0 and os.environ.get("PASCO_BENCH_GROUPS"):
+        for key, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[:40]:
+            log(f"  conv group {g['kind']:5s} n_out~{g['meta']['n_out']:8d} K={g['meta']['K']:3d} {g['meta']['Cin']:4d}->{g['meta']['Cout']:4d}: "
+                f"{g['n']:3d} launches, {g['ms'] / a.steps:7.2f} ms/step, {g['flops'] / g['ms'] / 1e9:6.1f} useful TFLOP/s")
     hbm_peak, tf_peak, peak_src = _peaks()
     roof = None
     if groups:
