@@ -177,6 +177,15 @@ int pasco_scatter_max(const float* src, const int64_t* index, int64_t n, int32_t
 int pasco_bn_stats(const float* x, int64_t n, int32_t C, double* stats, pasco_stream_t s);
 int pasco_affine_act(const float* x, int64_t n, int32_t C, const float* scale, const float* shift, int32_t act,
                      const float* residual, float* y, pasco_stream_t s);
+/* per-channel coefficients in one launch each: stats -> scale/shift (+ mean, rstd, running-statistics update);
+ * backward sums -> (ca, cb, cc) of dx = ca*dz + cb*x + cc and the gamma/beta gradients (divided by grad_div).
+ * count_dev (device double, e.g. the all-reduced SyncBatchNorm row count) overrides `count` when not NULL.       */
+int pasco_bn_finalize(const double* stats, const double* count_dev, double count, int32_t C, const float* gamma,
+                      const float* beta, float eps, float momentum, float* scale, float* shift, float* mean, float* rstd,
+                      float* running_mean, float* running_var, pasco_stream_t s);
+int pasco_bn_bwd_coefs(const double* sums, const double* count_dev, double count, int32_t C, const float* gamma,
+                       const float* mean, const float* rstd, float grad_div, float* ca, float* cb, float* cc, float* ggamma,
+                       float* gbeta, pasco_stream_t s);
 /* backward: given dy, x (pre-BN), scale/shift/act → sums float64[2*C] = (Σ dz, Σ dz·x̂·…) and dx */
 int pasco_bn_bwd_reduce(const float* dy, const float* x, int64_t n, int32_t C, const float* scale,
                         const float* shift, int32_t act, double* sums, pasco_stream_t s);

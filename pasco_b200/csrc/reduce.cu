@@ -162,6 +162,72 @@ extern "C" int pasco_bn_stats(const float* x, int64_t n, int32_t C, double* stat
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// per-channel coefficient kernels: everything between the column sums and the apply pass in ONE launch (was ~15 tiny
+// fp64 torch kernels per layer and the host-side bottleneck of the backward pass)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bn_finalize(const double* __restrict__ stats, const double* __restrict__ count_dev, double count, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                              float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                              float* __restrict__ rstd_out, float* __restrict__ run_mean, float* __restrict__ run_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = count_dev ? *count_dev : count;
+  const double mean = stats[c] / n;
+  double var = stats[C + c] / n - mean * mean;
+  if (var < 0) var = 0;
+  const double rstd = rsqrt(var + (double)eps);
+  const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+  scale[c] = (float)(g * rstd);
+  shift[c] = (float)(b - mean * g * rstd);
+  mean_out[c] = (float)mean;
+  rstd_out[c] = (float)rstd;
+  if (run_mean) {
+    const double unbias = n / (n > 1.0 ? n - 1.0 : 1.0);
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(var * unbias);
+  }
+}
+
+extern "C" int pasco_bn_finalize(const double* stats, const double* count_dev, double count, int32_t C, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* scale, float* shift, float* mean,
+                                 float* rstd, float* running_mean, float* running_var, pasco_stream_t s) {
+  if (C == 0) return 0;
+  k_bn_finalize<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(stats, count_dev, count, C, gamma, beta, eps, momentum, scale,
+                                                            shift, mean, rstd, running_mean, running_var);
+  PASCO_CHECK_LAUNCH("pasco_bn_finalize");
+  return 0;
+}
+
+// sums = (Σdz, Σdz·x) → dx = ca·dz + cb·x + cc coefficients and the parameter gradients
+__global__ void k_bn_bwd_coefs(const double* __restrict__ sums, const double* __restrict__ count_dev, double count, int C,
+                               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                               float grad_div, float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
+                               float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = count_dev ? *count_dev : count;
+  const double s_dz = sums[c], s_dzx = sums[C + c];
+  const double m = mean[c], r = rstd[c], g = gamma ? (double)gamma[c] : 1.0;
+  const double s_dzxhat = r * (s_dzx - m * s_dz);
+  const double m1 = s_dz / n, m2 = s_dzxhat / n;
+  ca[c] = (float)(g * r);
+  cb[c] = (float)(-g * r * r * m2);
+  cc[c] = (float)(g * r * (m * r * m2 - m1));
+  ggamma[c] = (float)(s_dzxhat / grad_div);
+  gbeta[c] = (float)(s_dz / grad_div);
+}
+
+extern "C" int pasco_bn_bwd_coefs(const double* sums, const double* count_dev, double count, int32_t C, const float* gamma,
+                                  const float* mean, const float* rstd, float grad_div, float* ca, float* cb, float* cc,
+                                  float* ggamma, float* gbeta, pasco_stream_t s) {
+  if (C == 0) return 0;
+  k_bn_bwd_coefs<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, count_dev, count, C, gamma, mean, rstd, grad_div, ca, cb,
+                                                             cc, ggamma, gbeta);
+  PASCO_CHECK_LAUNCH("pasco_bn_bwd_coefs");
+  return 0;
+}
+
 extern "C" int pasco_bn_bwd_reduce(const float* dy, const float* x, int64_t n, int32_t C, const float* scale,
                                    const float* shift, int32_t act, double* sums, pasco_stream_t s) {
   if (n == 0 || C == 0) return 0;

@@ -499,55 +499,51 @@ def affine_act(x, scale, shift, act: int = 0, residual=None):
 
 
 class BatchNormAct(torch.autograd.Function):
-    """y = act(BN(x)) with training-mode batch statistics over all rows (optionally summed over
-    ranks = SyncBatchNorm); one stats pass + one apply pass; backward one reduce + one apply."""
+    """y = act(BN(x)) with training-mode batch statistics over all rows (optionally summed over ranks =
+    SyncBatchNorm).  Forward: column sums → one coefficient kernel (scale/shift, mean/rstd, running statistics) →
+    one apply pass; backward: one reduce pass → one coefficient kernel → one apply pass."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, act, group):
+    def forward(ctx, x, gamma, beta, eps, act, group, running_mean=None, running_var=None, momentum=0.1):
         x = x.contiguous()
-        n = x.shape[0]
+        n, c = x.shape
+        dev = x.device
         stats = column_stats(x)
-        count = torch.tensor([float(n)], dtype=torch.float64, device=x.device)
+        count_dev = None
         if group is not None:
-            packed = torch.cat([stats.view(-1), count])
+            packed = torch.cat([stats.view(-1), torch.tensor([float(n)], dtype=torch.float64, device=dev)])
             torch.distributed.all_reduce(packed, group=group)
-            stats, count = packed[:-1].view(2, -1), packed[-1:]
-        mean = stats[0] / count
-        var = (stats[1] / count - mean * mean).clamp_(min=0)
-        rstd = torch.rsqrt(var + eps)
-        scale = (gamma.double() * rstd).float()
-        shift = (beta.double() - mean * gamma.double() * rstd).float()
+            stats, count_dev = packed[:-1].contiguous(), packed[-1:].contiguous()
+        scale, shift, mean, rstd = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
+        call("pasco_bn_finalize", ptr(stats), ptr(count_dev), C.c_double(float(n)), c, ptr(gamma), ptr(beta), C.c_float(eps),
+             C.c_float(momentum if momentum is not None else 0.1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+             ptr(running_mean), ptr(running_var))
         y = affine_act(x, scale, shift, act)
-        ctx.save_for_backward(x, gamma, scale, shift, mean.float(), rstd.float(), count)
-        ctx.act, ctx.group = act, group
-        ctx.mark_non_differentiable(mean, var, count)
-        return y, mean, var, count
+        ctx.save_for_backward(x, gamma, scale, shift, mean, rstd, count_dev)
+        ctx.act, ctx.group, ctx.n = act, group, n
+        return y
 
     @staticmethod
-    def backward(ctx, gy, *_):
-        x, gamma, scale, shift, mean, rstd, count = ctx.saved_tensors
+    def backward(ctx, gy):
+        x, gamma, scale, shift, mean, rstd, count_dev = ctx.saved_tensors
         gy = gy.contiguous()
-        sums = torch.zeros(2, x.shape[1], dtype=torch.float64, device=x.device)
-        call("pasco_bn_bwd_reduce", ptr(gy), ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ctx.act, ptr(sums))
+        c = x.shape[1]
+        dev = x.device
+        sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
+        call("pasco_bn_bwd_reduce", ptr(gy), ptr(x), x.shape[0], c, ptr(scale), ptr(shift), ctx.act, ptr(sums))
+        div = 1.0
         if ctx.group is not None:
+            # sums are global after the all-reduce; every rank then holds the global dgamma/dbeta, and the gradient
+            # all-reduce (mean over ranks) of the data-parallel step leaves them unchanged only if divided here
             torch.distributed.all_reduce(sums, group=ctx.group)
-        s_dz, s_dzx = sums[0], sums[1]
-        md, rd, gd = mean.double(), rstd.double(), gamma.double()
-        s_dzxhat = rd * (s_dzx - md * s_dz)
-        # NOTE: with a process group the reference (SyncBatchNorm) returns the *local* dgamma/dbeta
-        # contributions reduced by DDP; sums here are global, so divide back by world size in that case.
-        ggamma, gbeta = s_dzxhat, s_dz
-        if ctx.group is not None:
-            ws = torch.distributed.get_world_size(ctx.group)
-            ggamma, gbeta = ggamma / ws, gbeta / ws
-        m1, m2 = s_dz / count, s_dzxhat / count
-        ca = (gd * rd).float()
-        cb = (-gd * rd * rd * m2).float()
-        cc = (gd * rd * (md * rd * m2 - m1)).float()
+            div = float(torch.distributed.get_world_size(ctx.group))
+        ca, cb, cc, gg, gb = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(5))
+        call("pasco_bn_bwd_coefs", ptr(sums), ptr(count_dev), C.c_double(float(ctx.n)), c, ptr(gamma), ptr(mean), ptr(rstd),
+             C.c_float(div), ptr(ca), ptr(cb), ptr(cc), ptr(gg), ptr(gb))
         gx = torch.empty_like(x)
-        call("pasco_bn_bwd_apply", ptr(gy), ptr(x), x.shape[0], x.shape[1], ptr(scale), ptr(shift), ctx.act,
+        call("pasco_bn_bwd_apply", ptr(gy), ptr(x), x.shape[0], c, ptr(scale), ptr(shift), ctx.act,
              ptr(ca), ptr(cb), ptr(cc), ptr(gx))
-        return gx, ggamma.float(), gbeta.float(), None, None, None
+        return gx, gg, gb, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------

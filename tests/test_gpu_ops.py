@@ -314,11 +314,14 @@ def test_fused_batchnorm_act_forward_backward(ME, C, act):
     (yr * up.double()).sum().backward()
     xg = x.clone().cuda().requires_grad_(True)
     gg, bg = gamma.clone().cuda().requires_grad_(True), beta.clone().cuda().requires_grad_(True)
-    yg, mean, var, cnt = ops.BatchNormAct.apply(xg, gg, bg, 1e-5, act, None)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    yg = ops.BatchNormAct.apply(xg, gg, bg, 1e-5, act, None, rm, rv, 0.1)
     (yg * up.cuda()).sum().backward()
     assert relerr(yg, yr) <= TOL_TIGHT
     assert relerr(xg.grad, xr.grad) <= 1e-4 and relerr(gg.grad, gr.grad) <= 1e-4 and relerr(bg.grad, br.grad) <= 1e-4
-    assert relerr(mean, x.double().mean(0)) <= 1e-6 and relerr(var, x.double().var(0, unbiased=False)) <= 1e-5
+    # running statistics as torch.nn.BatchNorm1d keeps them (momentum 0.1, unbiased variance)
+    assert relerr(rm, 0.1 * x.double().mean(0)) <= 1e-5
+    assert relerr(rv, 0.9 + 0.1 * x.double().var(0, unbiased=True)) <= 1e-5
 
 
 # ------------------------------------------------------------------------------------------------
