@@ -140,9 +140,12 @@ int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int
                           const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
                           double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
                           pasco_stream_t s);
-/* Pre-split input path: x = hi + lo (bf16 planes [N, C] each, lo = NULL for precision 1), produced once per tensor —
- * optionally fused with y = act(x*scale + shift) (BatchNorm + ReLU of the producing layer) — so that the gather of the
- * convolution is a pure asynchronous copy (cp.async, zero fill for missing neighbours) into the UMMA tiles.          */
+/* Pre-split input path: x = hi + lo (bf16 planes, lo = NULL for precision 1), produced once per tensor — optionally
+ * fused with y = act(x*scale + shift) (BatchNorm + ReLU of the producing layer) — so that the gather of the convolution
+ * is done by the TMA engine (cp.async.bulk.tensor tile::gather4: 4 arbitrary rows per instruction, written straight
+ * into the swizzled UMMA tiles).  A plane holds N + PASCO_PLANE_PAD_ROWS rows of C bf16: pasco_split_planes zero-fills
+ * the pad, and the convolution redirects missing neighbours (-1) into it.                                           */
+#define PASCO_PLANE_PAD_ROWS 1024
 int pasco_split_planes(const float* x, int64_t n, int32_t C, int64_t pitch, const float* scale, const float* shift,
                        int32_t act, void* hi, void* lo, pasco_stream_t s);
 int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,

@@ -1,13 +1,20 @@
-// Sparse convolution on tcgen05 with PRE-SPLIT bf16 input planes and an asynchronous-copy gather (sm_100a).
+// Sparse convolution on tcgen05 with PRE-SPLIT bf16 input planes gathered by the TMA engine (sm_100a).
 //
 // Same output-stationary implicit GEMM, tile groups, weight-slice ring, TMEM double buffering, MMA issue and epilogue as
 // conv_tc.cu; what changes is the producer: activations are split x = hi + lo (bf16 each) ONCE per tensor by
 // k_split_planes (optionally fused with the BatchNorm affine + activation that produced them) instead of 27x inside
-// the gather, and a tile row becomes a pure 128-byte copy per plane: 16-byte cp.async (LDGSTS) straight into the
-// 128-byte-swizzled UMMA tile with zero fill for missing neighbours.  The gather warps issue ~1/3 of the instructions
-// of the register path and keep DEPTH slots in flight each.
+// the gather, and a 128-row A tile is then fetched by 32 `cp.async.bulk.tensor.2d.tile::gather4` instructions per plane:
+// each names 4 arbitrary row indices of the [N_in, Cin] plane (tensor-map box 64 x 1, SWIZZLE_128B) and the TMA unit
+// writes the four 128-byte rows straight into the swizzled UMMA tile.  No LSU instructions, registers or conversions on
+// the gather path.  Missing neighbours (-1) are redirected to a pad of PLANE_PAD all-zero rows behind the plane: the
+// TMA's own out-of-range zero fill costs ~9 ns per row per SM (4.5x slower than fetching), and ONE shared zero row
+// hot-spots an L2 slice (0.6 TB/s), while zero rows spread over the pad run at the full 10 TB/s (all measured).
+// Measured (tools/tma_gather_probe.cu): one warp sustains one gather4 per ~46 ns whatever the ring depth, and issuing
+// warps scale linearly (6 warps: 34 B/clk/SM, 9.6 TB/s over the GPU), so the 8 producer warps each own one
+// (stage, plane) in turn and 4 stages are in flight.
 #include "common.cuh"
 #include "umma.cuh"
+#include <cuda.h>
 
 using namespace pasco;
 using namespace umma;
@@ -22,9 +29,8 @@ constexpr int NUM_EPI_WARPS = 4;
 constexpr int MMA_WARP = NUM_GATHER_WARPS + NUM_EPI_WARPS;
 constexpr int LOAD_WARP = MMA_WARP + 1;
 constexpr int NUM_THREADS = (LOAD_WARP + 1) * 32;
-constexpr int ROWS_PER_WARP = BLOCK_M / NUM_GATHER_WARPS;
 constexpr int MAX_STAGES = 8;
-constexpr int IDX_RING = 8;
+constexpr int PLANE_PAD = 1024;   // == PASCO_PLANE_PAD_ROWS: zero rows behind every plane (power of two)
 
 struct PlaneParams {
   const __nv_bfloat16* hi;   // [N_in, Cin]
@@ -35,27 +41,54 @@ struct PlaneParams {
   float* out;
   int64_t n_out;
   int64_t out_pitch;
+  int zero_row;              // first row of the zero pad (= n_in)
   int K, Cin, Cout;
   int sa, sb, tiles_per_group, tmem_cols;
   int koff_base, koff_step;
 };
 
-__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// the driver's tensor-map encoder, fetched through the runtime so that the library does not link libcuda
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// [n_rows, C] bf16 plane, box = 64 channels x 1 row (the gather4 box is one row; 4 rows are named per instruction)
+bool make_plane_map(CUtensorMap* tm, const void* base, int64_t n_rows, int C) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KBLK, 1};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // fp32 [N, C] (row pitch `pitch`) → bf16 planes hi (and lo = bf16(x − hi)); optional y = act(x*scale + shift) first
 __global__ void k_split_planes(const float* __restrict__ x, int64_t n, int C, int64_t pitch, const float* __restrict__ scale,
                                const float* __restrict__ shift, int act, __nv_bfloat16* __restrict__ hi,
                                __nv_bfloat16* __restrict__ lo) {
   const int cv = C >> 2;
-  const int64_t total = n * cv;
+  const int64_t total = (n + PLANE_PAD) * cv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / cv;
     const int c = (int)(t - r * cv) << 2;
+    if (r >= n) {                                  // the zero pad behind the plane
+      *reinterpret_cast<uint2*>(hi + r * C + c) = make_uint2(0u, 0u);
+      if (lo) *reinterpret_cast<uint2*>(lo + r * C + c) = make_uint2(0u, 0u);
+      continue;
+    }
     float4 v = __ldg(reinterpret_cast<const float4*>(x + r * pitch + c));
     if (scale) {
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), sh = __ldg(reinterpret_cast<const float4*>(shift + c));
@@ -79,7 +112,8 @@ __global__ void k_split_planes(const float* __restrict__ x, int64_t n, int C, in
 }
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_constant__ PlaneParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_constant__ PlaneParams p, const __grid_constant__ CUtensorMap tm_hi,
+                                                                const __grid_constant__ CUtensorMap tm_lo) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int n_op = (NSPLIT == 3) ? 2 : 1;
@@ -89,8 +123,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
   const int T = p.tiles_per_group;
   uint8_t* a_smem = smem;                                           // [sa][A_hi | A_lo]
   uint8_t* b_smem = smem + (size_t)p.sa * a_stage_bytes;            // [sb][B_hi | B_lo]
-  int* idx_ring = reinterpret_cast<int*>(b_smem + (size_t)p.sb * b_stage_bytes);   // [IDX_RING][T*128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_ring + IDX_RING * T * BLOCK_M);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)p.sb * b_stage_bytes);
   uint64_t* afull = bars;                         // [MAX_STAGES]
   uint64_t* aempty = bars + MAX_STAGES;           // [MAX_STAGES]
   uint64_t* bfull = bars + 2 * MAX_STAGES;        // [MAX_STAGES]
@@ -107,7 +140,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(smem_u32(afull + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(afull + s), n_op);   // one arrive.expect_tx per plane
       mbar_init(smem_u32(aempty + s), 1);
       mbar_init(smem_u32(bfull + s), 1);
       mbar_init(smem_u32(bempty + s), 1);
@@ -125,119 +158,86 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < NUM_GATHER_WARPS) {
-    // ===================================== gather producers (async copies) =====================================
-    // The input arrives pre-split into bf16 planes (hi, lo) [N_in, Cin], so a tile row is a pure 128-byte copy per
-    // plane and 64-channel block: 16-byte cp.async (LDGSTS) straight into the swizzled UMMA tile, zero-filled
-    // (src-size 0) where the neighbour is missing.  No registers, no conversion: DEPTH slots are in flight per warp.
-    constexpr int DEPTH = 3;                                   // slots in flight per warp (bounded by the ring: sa - 1)
-    const int depth = p.sa - 1 < DEPTH ? p.sa - 1 : DEPTH;
-    const int crow = lane >> 3;      // 4 rows per instruction
-    const int cchunk = lane & 7;     // 16-byte chunk of the 128-byte row segment
-    const int PE = (DEPTH + 1 + T * KB - 1) / (T * KB) + 1;   // index-ring prefetch distance in (group,k) entries
-
-    auto prefetch_idx = [&](int64_t group, int k, int gk, int t_eff) {   // joins the current cp.async group (no commit)
-      int* dst = idx_ring + (gk % IDX_RING) * T * BLOCK_M;
-      for (int t = lane >> 4; t < t_eff; t += 2) {
-        const int64_t row = (group * T + t) * BLOCK_M + warp * ROWS_PER_WARP + (lane & 15);
-        int* d = dst + t * BLOCK_M + warp * ROWS_PER_WARP + (lane & 15);
-        if (row < p.n_out) {
-          if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
-          else *d = (int)row;
-        } else {
-          *d = -1;
-        }
-      }
-    };
-    // cursor over (group, k, kb, t)
-    int64_t i_group = blockIdx.x;
-    int i_k = 0, i_kb = 0, i_t = 0, i_gk = 0;
-    int64_t rem0 = num_tiles - i_group * T;
-    int i_teff = rem0 < T ? (int)rem0 : T;
-    bool i_valid = i_group < num_groups;
-    // prefetch cursor over (group, k), PE entries ahead of the issue cursor
-    int64_t f_group = blockIdx.x;
-    int f_k = 0, f_gk = 0;
-    auto prefetch_next_entry = [&]() {
-      if (f_group < num_groups) {
-        int64_t rem = num_tiles - f_group * T;
-        prefetch_idx(f_group, f_k, f_gk, rem < T ? (int)rem : T);
-      }
-      ++f_gk;
-      if (++f_k == p.K) {
-        f_k = 0;
-        f_group += gridDim.x;
-      }
-    };
-    int st_i = 0, st_p = 0;          // issue / publish stage
-    uint32_t ph_i = 0;
-    int in_flight = 0;
-    auto publish = [&]() {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(afull + st_p));
-      if (++st_p == p.sa) st_p = 0;
-      --in_flight;
-    };
-    if (i_valid) {
-      for (int a = 0; a < PE; ++a) prefetch_next_entry();
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncwarp();
-      while (i_valid) {
-        if (i_kb == 0 && i_t == 0) prefetch_next_entry();            // keep the ring PE entries ahead
-        mbar_wait(smem_u32(aempty + st_i), ph_i ^ 1);
-        const int* irow = idx_ring + (i_gk % IDX_RING) * T * BLOCK_M + i_t * BLOCK_M + warp * ROWS_PER_WARP;
-        const uint32_t dst0 = smem_u32(a_smem + (size_t)st_i * a_stage_bytes);
-        const int64_t coff = (int64_t)i_kb * KBLK + cchunk * 8;        // bf16 elements
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 4 + crow;                                  // row within this warp's 16
-          const int src = irow[r];
-          const uint32_t trow = (uint32_t)(warp * ROWS_PER_WARP + r);
-          const uint32_t off = trow * 128u + (((uint32_t)cchunk ^ (trow & 7u)) << 4);
-          const int64_t e = (int64_t)(src >= 0 ? src : 0) * p.Cin + coff;
-          const uint32_t nbytes = src >= 0 ? 16u : 0u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + off), "l"(p.hi + e), "r"(nbytes) : "memory");
-          if (NSPLIT == 3)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + A_TILE_BYTES + off), "l"(p.lo + e), "r"(nbytes) : "memory");
-        }
-        cp_async_commit();
-        ++in_flight;
-        if (++st_i == p.sa) {
-          st_i = 0;
-          ph_i ^= 1;
-        }
-        // advance the issue cursor
-        if (++i_t == i_teff) {
-          i_t = 0;
-          if (++i_kb == KB) {
-            i_kb = 0;
-            ++i_gk;
-            if (++i_k == p.K) {
-              i_k = 0;
-              i_group += gridDim.x;
-              i_valid = i_group < num_groups;
-              if (i_valid) {
-                int64_t rem = num_tiles - i_group * T;
-                i_teff = rem < T ? (int)rem : T;
+    // ===================================== gather producers (TMA gather4) =====================================
+    // Stage n of the ring is the A tile of (group, k, kb, t) in MMA order.  Warp w owns plane (w % n_op) of the stages
+    // n ≡ w / n_op (mod NUM_GATHER_WARPS / n_op); lane l fetches tile rows 4l..4l+3 with one gather4.
+    const int my_pl = (n_op == 2) ? (warp & 1) : 0;
+    const int my_first = (n_op == 2) ? (warp >> 1) : warp;
+    constexpr int MOD = NUM_GATHER_WARPS / n_op;
+    const CUtensorMap* tm = my_pl ? &tm_lo : &tm_hi;
+    // cursor over stages (scalars; advanced MOD stages at a time)
+    int64_t c_group = blockIdx.x;
+    int c_k = 0, c_kb = 0, c_t = 0;
+    int64_t rem0 = num_tiles - c_group * T;
+    int c_teff = rem0 < T ? (int)rem0 : T;
+    bool c_valid = c_group < num_groups;
+    auto advance = [&](int steps) {
+      for (int s_ = 0; s_ < steps && c_valid; ++s_) {
+        if (++c_t == c_teff) {
+          c_t = 0;
+          if (++c_kb == KB) {
+            c_kb = 0;
+            if (++c_k == p.K) {
+              c_k = 0;
+              c_group += gridDim.x;
+              c_valid = c_group < num_groups;
+              if (c_valid) {
+                const int64_t rem = num_tiles - c_group * T;
+                c_teff = rem < T ? (int)rem : T;
               }
             }
           }
         }
-        if (in_flight > depth) {
-          if (depth >= 3) cp_async_wait<3>();
-          else if (depth == 2) cp_async_wait<2>();
-          else if (depth == 1) cp_async_wait<1>();
-          else cp_async_wait<0>();
-          publish();
-        }
       }
-      // drain
-      if (in_flight >= 3) { cp_async_wait<2>(); publish(); }
-      if (in_flight >= 2) { cp_async_wait<1>(); publish(); }
-      if (in_flight >= 1) { cp_async_wait<0>(); publish(); }
+    };
+    auto load_idx = [&]() -> int4 {
+      const int64_t row = (c_group * T + c_t) * BLOCK_M + 4 * lane;
+      const int z = p.zero_row + ((4 * lane + 128 * (c_k & 7)) & (PLANE_PAD - 1));   // my 4 zero rows of the pad
+      int4 v;
+      if (p.nbr) {
+        const int32_t* src = p.nbr + (int64_t)c_k * p.n_out + row;
+        v.x = row + 0 < p.n_out ? __ldg(src + 0) : -1;
+        v.y = row + 1 < p.n_out ? __ldg(src + 1) : -1;
+        v.z = row + 2 < p.n_out ? __ldg(src + 2) : -1;
+        v.w = row + 3 < p.n_out ? __ldg(src + 3) : -1;
+      } else {
+        v.x = row + 0 < p.n_out ? (int)row + 0 : -1;
+        v.y = row + 1 < p.n_out ? (int)row + 1 : -1;
+        v.z = row + 2 < p.n_out ? (int)row + 2 : -1;
+        v.w = row + 3 < p.n_out ? (int)row + 3 : -1;
+      }
+      v.x = v.x < 0 ? z + 0 : v.x;
+      v.y = v.y < 0 ? z + 1 : v.y;
+      v.z = v.z < 0 ? z + 2 : v.z;
+      v.w = v.w < 0 ? z + 3 : v.w;
+      return v;
+    };
+    advance(my_first);
+    int slot = my_first % p.sa;
+    uint32_t phase = (uint32_t)(my_first / p.sa) & 1u;
+    int4 idx = make_int4(0, 0, 0, 0);
+    if (c_valid) idx = load_idx();
+    while (c_valid) {
+      const int col = c_kb * KBLK;
+      const uint32_t dst = smem_u32(a_smem + (size_t)slot * a_stage_bytes + (size_t)my_pl * A_TILE_BYTES) + (uint32_t)lane * 512u;
+      const uint32_t bar = smem_u32(afull + slot);
+      const uint32_t ebar = smem_u32(aempty + slot);
+      const uint32_t eph = phase ^ 1u;
+      const int4 cur = idx;
+      advance(MOD);                                  // index prefetch of my next stage overlaps the wait + issue below
+      if (c_valid) idx = load_idx();
+      mbar_wait(ebar, eph);
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)A_TILE_BYTES);
+      __syncwarp();
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+          ::"r"(dst), "l"(tm), "r"(col), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w), "r"(bar) : "memory");
+      slot += MOD;
+      while (slot >= p.sa) {
+        slot -= p.sa;
+        phase ^= 1u;
+      }
     }
-    cp_async_wait<0>();
   } else if (warp == LOAD_WARP) {
     // ===================================== weight-slice loader =====================================
     if (lane == 0) {
@@ -386,8 +386,7 @@ int pow2_cols_p(int c) {
 extern "C" int pasco_split_planes(const float* x, int64_t n, int32_t C, int64_t pitch, const float* scale, const float* shift,
                                   int32_t act, void* hi, void* lo, pasco_stream_t s) {
   PASCO_CHECK_ARG(C % 4 == 0 && (pitch == 0 || pitch % 4 == 0), "pasco_split_planes: C and pitch must be multiples of 4");
-  if (n == 0) return 0;
-  k_split_planes<<<grid_for(n * (C / 4), 256), 256, 0, (cudaStream_t)s>>>(x, n, C, pitch > 0 ? pitch : C, scale, shift, act,
+  k_split_planes<<<grid_for((n + PLANE_PAD) * (C / 4), 256), 256, 0, (cudaStream_t)s>>>(x, n, C, pitch > 0 ? pitch : C, scale, shift, act,
                                                                       (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   PASCO_CHECK_LAUNCH("pasco_split_planes");
   return 0;
@@ -402,8 +401,12 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_planes: Cin (%d) must be a multiple of 64", Cin);
   PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_planes: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
   PASCO_CHECK_ARG(K >= 1 && K <= 1024, "pasco_conv_forward_planes: K (%d) out of range", K);
-  (void)n_in;
   if (n_out == 0) return 0;
+  CUtensorMap tm_hi, tm_lo;
+  if (!make_plane_map(&tm_hi, hi, n_in + PLANE_PAD, Cin) || !make_plane_map(&tm_lo, lo ? lo : hi, n_in + PLANE_PAD, Cin)) {
+    set_error("pasco_conv_forward_planes: cuTensorMapEncodeTiled failed (n_in=%lld, Cin=%d)", (long long)n_in, Cin);
+    return -1;
+  }
   int dev = 0, smem_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -414,15 +417,14 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   if (T < 1) T = 1;
   if (T > 4) T = 4;
   while (T > 1 && tiles < (int64_t)T * num_sms()) T >>= 1;
-  const int idx_bytes = IDX_RING * T * BLOCK_M * 4;
-  const int fixed = 1024 + idx_bytes + (4 * MAX_STAGES + 4) * 8 + 16;
+  const int fixed = 1024 + (4 * MAX_STAGES + 4) * 8 + 16;
   int sb = 2;
   int sa = (smem_optin - fixed - sb * b_stage) / a_stage;
   if (sa > MAX_STAGES) sa = MAX_STAGES;
   PASCO_CHECK_ARG(sa >= 2, "pasco_conv_forward_planes: not enough shared memory (Cout=%d)", Cout);
   PlaneParams p;
   p.hi = (const __nv_bfloat16*)hi; p.lo = (const __nv_bfloat16*)lo; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w;
-  p.bias = bias; p.out = out; p.n_out = n_out; p.out_pitch = out_pitch > 0 ? out_pitch : Cout;
+  p.bias = bias; p.out = out; p.n_out = n_out; p.zero_row = (int)n_in; p.out_pitch = out_pitch > 0 ? out_pitch : Cout;
   p.K = K; p.Cin = Cin; p.Cout = Cout;
   p.sa = sa; p.sb = sb; p.tiles_per_group = T; p.tmem_cols = pow2_cols_p(2 * T * Cout);
   p.koff_base = 0; p.koff_step = 1;
@@ -440,7 +442,7 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   int grid = (int)(groups < num_sms() ? groups : num_sms());
   auto launch = [&](auto kern) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess) kern<<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+    if (err == cudaSuccess) kern<<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p, tm_hi, tm_lo);
     return err;
   };
   cudaError_t e = precision == 3 ? launch(k_conv_planes<3>) : launch(k_conv_planes<1>);

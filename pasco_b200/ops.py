@@ -322,11 +322,15 @@ def use_planes(flag: bool) -> None:
     _USE_PLANES = bool(flag)
 
 
+PLANE_PAD = 1024    # PASCO_PLANE_PAD_ROWS
+
+
 def split_planes(x: torch.Tensor, scale=None, shift=None, act: int = 0):
-    """x fp32 [N,C] → (hi, lo) bf16 planes of act(x*scale+shift); lo is None in bf16 mode."""
+    """x fp32 [N,C] → (hi, lo) bf16 planes of act(x*scale+shift), each N + PLANE_PAD rows (the pad is zero: missing
+    neighbours are gathered from it); lo is None in bf16 mode."""
     n, c = x.shape
-    hi = torch.empty(n, c, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(n, c, dtype=torch.bfloat16, device=x.device) if _PRECISION == 3 else None
+    hi = torch.empty(n + PLANE_PAD, c, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(n + PLANE_PAD, c, dtype=torch.bfloat16, device=x.device) if _PRECISION == 3 else None
     call("pasco_split_planes", ptr(x), n, c, 0, ptr(scale), ptr(shift), act, ptr(hi), ptr(lo))
     return hi, lo
 

@@ -57,6 +57,41 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 lines.append(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
 lines.append(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=70))
+lines.append(prof.key_averages().table(sort_by="cpu_time_total", row_limit=40, max_name_column_width=70))
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+busy = sum(e.time_range.end - e.time_range.start for e in ev) / 1e3
+span = (max(e.time_range.end for e in ev) - min(e.time_range.start for e in ev)) / 1e3
+lines.insert(1, f"GPU busy {busy:.1f} ms of a {span:.1f} ms span ({len(ev)} kernels/copies)")
+# GPU idle gaps: which CPU-side op was running while the GPU had nothing to do
+ks = sorted(((e.time_range.start, e.time_range.end) for e in ev))
+cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU and e.time_range.end - e.time_range.start > 0]
+cpu.sort(key=lambda e: e.time_range.start)
+import bisect, collections
+starts = [e.time_range.start for e in cpu]
+gaps = collections.Counter()
+gap_n = collections.Counter()
+end = ks[0][1]
+total_gap = 0.0
+for st, en in ks[1:]:
+    if st - end > 5:        # µs
+        g = st - end
+        total_gap += g
+        mid = end + g / 2
+        i = bisect.bisect_right(starts, mid)
+        # outermost-but-informative: the LONGEST enclosing op that is not a profiler/step wrapper, and the innermost
+        encl = [c for c in cpu[max(0, i - 400):i] if c.time_range.start <= mid <= c.time_range.end]
+        if encl:
+            encl.sort(key=lambda c: c.time_range.end - c.time_range.start)
+            inner = encl[0].name
+            outer = next((c.name for c in reversed(encl) if not c.name.startswith("ProfilerStep")), inner)
+            key = f"{outer[:48]} > {inner[:40]}"
+        else:
+            key = "(no CPU op: python between ops)"
+        gaps[key] += g
+        gap_n[key] += 1
+    end = max(end, en)
+lines.insert(2, f"GPU idle (gaps > 5 us): {total_gap / 1e3:.1f} ms; by enclosing CPU op (outermost > innermost):\n" + "\n".join(
+    f"   {v / 1e3:7.2f} ms  {gap_n[k]:4d}x  {k}" for k, v in gaps.most_common(40)))
 os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
 open(a.out, "w").write("\n".join(lines))
 print(lines[0])
