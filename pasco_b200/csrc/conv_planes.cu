@@ -163,14 +163,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
     // n ≡ w / n_op (mod NUM_GATHER_WARPS / n_op); lane l fetches tile rows 4l..4l+3 with one gather4.
     const int my_pl = (n_op == 2) ? (warp & 1) : 0;
     const int my_first = (n_op == 2) ? (warp >> 1) : warp;
-    constexpr int MOD = NUM_GATHER_WARPS / n_op;
+    // a waiter may be at most one mbarrier phase ahead: the stride between a warp's stages must not exceed the ring
+    const int MOD = (NUM_GATHER_WARPS / n_op) < p.sa ? (NUM_GATHER_WARPS / n_op) : p.sa;
     const CUtensorMap* tm = my_pl ? &tm_lo : &tm_hi;
     // cursor over stages (scalars; advanced MOD stages at a time)
     int64_t c_group = blockIdx.x;
     int c_k = 0, c_kb = 0, c_t = 0;
     int64_t rem0 = num_tiles - c_group * T;
     int c_teff = rem0 < T ? (int)rem0 : T;
-    bool c_valid = c_group < num_groups;
+    bool c_valid = c_group < num_groups && my_first < MOD;
     auto advance = [&](int steps) {
       for (int s_ = 0; s_ < steps && c_valid; ++s_) {
         if (++c_t == c_teff) {

@@ -23,17 +23,18 @@ def lovasz_softmax_present(probs: torch.Tensor, labels: torch.Tensor) -> torch.T
     n_cls = probs.shape[1]
     if probs.shape[0] == 0:
         return probs.sum() * 0
-    fg = F.one_hot(labels, n_cls).to(probs.dtype)                   # [P,C]
-    present = (fg.sum(0) > 0).to(probs.dtype)                       # [C]
-    err = (fg - probs).abs()
-    err_sorted, perm = torch.sort(err, dim=0, descending=True)
-    fg_sorted = fg.gather(0, perm)
-    gts = fg_sorted.sum(0, keepdim=True)
-    inter = gts - fg_sorted.cumsum(0)
-    union = gts + (1 - fg_sorted).cumsum(0)
+    cls = torch.arange(n_cls, device=labels.device).view(-1, 1)
+    fg = (labels.view(1, -1) == cls).to(probs.dtype)                # [C,P]: class-major so that sort / cumsum run along
+    present = (fg.sum(1) > 0).to(probs.dtype)                       # the contiguous dimension
+    err = (fg - probs.t()).abs()
+    err_sorted, perm = torch.sort(err, dim=1, descending=True)
+    fg_sorted = fg.gather(1, perm)
+    gts = fg_sorted.sum(1, keepdim=True)
+    inter = gts - fg_sorted.cumsum(1)
+    union = gts + (1 - fg_sorted).cumsum(1)
     jac = 1.0 - inter / union
-    jac = torch.cat([jac[:1], jac[1:] - jac[:-1]])
-    per_class = (err_sorted * jac).sum(0)
+    jac = torch.cat([jac[:, :1], jac[:, 1:] - jac[:, :-1]], 1)
+    per_class = (err_sorted * jac).sum(1)
     return (per_class * present).sum() / present.sum().clamp(min=1)
 
 
