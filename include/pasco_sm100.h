@@ -140,6 +140,12 @@ int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int
                           const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
                           double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
                           pasco_stream_t s);
+/* Two kernels implement pasco_conv_forward_tc: the register-gather kernel (variant 0, default) and a TMA-gather kernel
+ * (variant 1: tile::gather4 fetches the neighbour rows into a raw shared-memory ring, warps only convert; used when
+ * Cout <= 128 leaves room for that ring, otherwise variant 0 runs).  Results are identical bit for bit (same operand
+ * split, same MMA order); measured speeds are in DESIGN.md section 3.4.                                             */
+int pasco_conv_set_variant(int32_t variant);
+
 /* Pre-split input path: x = hi + lo (bf16 planes, lo = NULL for precision 1), produced once per tensor — optionally
  * fused with y = act(x*scale + shift) (BatchNorm + ReLU of the producing layer) — so that the gather of the convolution
  * is done by the TMA engine (cp.async.bulk.tensor tile::gather4: 4 arbitrary rows per instruction, written straight

@@ -14,7 +14,7 @@
 // (stage, plane) in turn and 4 stages are in flight.
 #include "common.cuh"
 #include "umma.cuh"
-#include <cuda.h>
+#include "tma.cuh"
 
 using namespace pasco;
 using namespace umma;
@@ -47,32 +47,10 @@ struct PlaneParams {
   int koff_base, koff_step;
 };
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// the driver's tensor-map encoder, fetched through the runtime so that the library does not link libcuda
-EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
-    return (EncodeTiledFn)f;
-  }();
-  return fn;
-}
-
-// [n_rows, C] bf16 plane, box = 64 channels x 1 row (the gather4 box is one row; 4 rows are named per instruction)
+// [n_rows, C] bf16 plane, box = 64 channels x 1 row, 128-byte swizzle (= the UMMA K-major tile layout)
 bool make_plane_map(CUtensorMap* tm, const void* base, int64_t n_rows, int C) {
-  EncodeTiledFn enc = tensor_map_encoder();
-  if (!enc) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)n_rows};
-  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-  cuuint32_t box[2] = {(cuuint32_t)KBLK, 1};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return tma::make_row_gather_map(tm, base, n_rows, C, (int64_t)C * 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, KBLK,
+                                  CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // fp32 [N, C] (row pitch `pitch`) → bf16 planes hi (and lo = bf16(x − hi)); optional y = act(x*scale + shift) first
@@ -230,9 +208,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_planes(const __grid_con
       mbar_wait(ebar, eph);
       if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)A_TILE_BYTES);
       __syncwarp();
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-          ::"r"(dst), "l"(tm), "r"(col), "r"(cur.x), "r"(cur.y), "r"(cur.z), "r"(cur.w), "r"(bar) : "memory");
+      tma::gather4(dst, tm, col, cur.x, cur.y, cur.z, cur.w, bar);
       slot += MOD;
       while (slot >= p.sa) {
         slot -= p.sa;

@@ -317,6 +317,13 @@ class PackedWeights:
         return buf
 
 
+def set_conv_variant(variant: int) -> None:
+    """0 (default) = register-gather conv kernel, 1 = TMA-gather kernel where eligible (Cout <= 128)."""
+    from ._lib import load
+    if load().pasco_conv_set_variant(int(variant)) != 0:
+        raise RuntimeError(load().pasco_last_error().decode())
+
+
 def use_planes(flag: bool) -> None:
     global _USE_PLANES
     _USE_PLANES = bool(flag)

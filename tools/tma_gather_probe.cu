@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NW * 32) k_stream(const __grid_constant__ CUte
 }
 
 // ---- (3) issue scaling: NW warps, LANES active lanes each, one buffer per warp (issue → wait → issue ...)
-template <int NW, int LANES>
+template <int NW, int LANES, int G4B = 512>
 __global__ void __launch_bounds__(NW * 32) k_issue(const __grid_constant__ CUtensorMap tm_hi, const int* __restrict__ idx, int iters,
                                                    int n_idx_tiles, unsigned long long* sink) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(NW * 32) k_issue(const __grid_constant__ CUten
   if (threadIdx.x == 0) { for (int s = 0; s < NW; ++s) mbar_init(&full[s], 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* mine = base + warp * (LANES * 512);
+  uint8_t* mine = base + warp * (LANES * G4B);
   unsigned long long acc = 0;
   for (int it = 0; it < iters; ++it) {
     const int tile = ((blockIdx.x * NW + warp) * iters + it) % n_idx_tiles;
     const int4 r = *(const int4*)(idx + (size_t)tile * 128 + lane * 4);
-    if (lane == 0) mbar_expect(&full[warp], LANES * 512);
+    if (lane == 0) mbar_expect(&full[warp], LANES * G4B);
     __syncwarp();
-    if (lane < LANES) gather4(mine + lane * 512, &tm_hi, 0, r.x, r.y, r.z, r.w, &full[warp]);
+    if (lane < LANES) gather4(mine + lane * G4B, &tm_hi, 0, r.x, r.y, r.z, r.w, &full[warp]);
     while (!mbar_try(&full[warp], it & 1)) {}
     acc += *(volatile uint32_t*)(mine + (lane % LANES) * 64);
     __syncwarp();
@@ -190,31 +190,40 @@ int main() {
   };
   fill(10, -1, false);
   run(k_stream<6>, 6, "random rows, 10% missing(-1)");
-  auto run2 = [&](auto kern, int nw, int lanes) {
-    const int smem = nw * lanes * 512 + 1024;
+  auto run2 = [&](auto kern, int nw, int lanes, int g4b, const CUtensorMap& tmx) {
+    const int smem = nw * lanes * g4b + 1024;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int iters = 2000, grid = 148;
-    kern<<<grid, nw * 32, smem>>>(tm_hi, d_idx, 50, n_tiles, d_sink);
+    kern<<<grid, nw * 32, smem>>>(tmx, d_idx, 50, n_tiles, d_sink);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    kern<<<grid, nw * 32, smem>>>(tm_hi, d_idx, iters, n_tiles, d_sink);
+    kern<<<grid, nw * 32, smem>>>(tmx, d_idx, iters, n_tiles, d_sink);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double n4 = (double)nw * lanes * iters;
     printf("issue->wait loop, %2d warps x %2d lanes: %.3f ms, %.1f ns per gather4 per SM, %.1f GB/s aggregate, %.2f us per warp round\n", nw,
-           lanes, ms, ms * 1e6 / n4, n4 * 512 * 148 / ms / 1e6, ms * 1e3 / iters);
+           lanes, ms, ms * 1e6 / n4, n4 * g4b * 148 / ms / 1e6, ms * 1e3 / iters);
   };
-  run2(k_issue<1, 32>, 1, 32);
-  run2(k_issue<1, 16>, 1, 16);
-  run2(k_issue<1, 8>, 1, 8);
-  run2(k_issue<1, 1>, 1, 1);
-  run2(k_issue<4, 32>, 4, 32);
-  run2(k_issue<8, 32>, 8, 32);
-  run2(k_issue<12, 32>, 12, 32);
-  run2(k_issue<8, 16>, 8, 16);
-  run2(k_issue<16, 16>, 16, 16);
-  run2(k_issue<16, 8>, 16, 8);
-  run2(k_issue<24, 8>, 24, 8);
+  run2(k_issue<4, 32>, 4, 32, 512, tm_hi);
+  run2(k_issue<8, 32>, 8, 32, 512, tm_hi);
+  // fp32 rows of 64 channels (256 B), no swizzle: 1 KB per gather4
+  float* d_f32; CK(cudaMalloc(&d_f32, (size_t)N * 64 * 4)); CK(cudaMemset(d_f32, 0, (size_t)N * 64 * 4));
+  CUtensorMap tm_f32;
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)N};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_f32, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("fp32 map encode rc=%d\n", (int)r);
+  }
+  fill(0, -1, false);
+  printf("fp32 256-B rows, 1 KB per gather4:\n");
+  run2(k_issue<1, 32, 1024>, 1, 32, 1024, tm_f32);
+  run2(k_issue<2, 32, 1024>, 2, 32, 1024, tm_f32);
+  run2(k_issue<4, 32, 1024>, 4, 32, 1024, tm_f32);
+  run2(k_issue<6, 32, 1024>, 6, 32, 1024, tm_f32);
   return 0;
 }
