@@ -33,13 +33,17 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int KBLK = 64;                    // channels per K-block (= one 128-byte swizzle row of bf16)
 constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB
-constexpr int NUM_GATHER_WARPS = 8;                             // 16 tile rows each
-constexpr int NUM_EPI_WARPS = 4;                                // warps 8-11: warp % 4 = TMEM lane quadrant
-constexpr int MMA_WARP = NUM_GATHER_WARPS + NUM_EPI_WARPS;      // 12
-constexpr int LOAD_WARP = MMA_WARP + 1;                        // 13
-constexpr int NUM_THREADS = (LOAD_WARP + 1) * 32;              // 448
-constexpr int ROWS_PER_WARP = BLOCK_M / NUM_GATHER_WARPS;       // 16
-constexpr int LOADS_PER_SLOT = ROWS_PER_WARP / 2;               // 8 float4 per lane per slot
+#ifndef PASCO_GATHER_WARPS
+#define PASCO_GATHER_WARPS 8
+#endif
+constexpr int NUM_GATHER_WARPS = PASCO_GATHER_WARPS;            // 8 (16 tile rows each) or 16 (8 rows each)
+constexpr int NUM_EPI_WARPS = 4;                                // next 4 warps: warp % 4 = TMEM lane quadrant
+constexpr int MMA_WARP = NUM_GATHER_WARPS + NUM_EPI_WARPS;
+constexpr int LOAD_WARP = MMA_WARP + 1;
+constexpr int NUM_THREADS = (LOAD_WARP + 1) * 32;              // 448 / 704
+constexpr int ROWS_PER_WARP = BLOCK_M / NUM_GATHER_WARPS;       // 16 / 8
+constexpr int LOADS_PER_SLOT = ROWS_PER_WARP / 2;               // float4 per lane per slot
+constexpr int TILES_PER_IDX_STEP = 32 / ROWS_PER_WARP;          // tiles whose indices one warp-wide cp.async covers
 constexpr int MAX_STAGES = 8;
 
 struct ConvParams {
@@ -325,9 +329,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     auto prefetch_idx = [&](int64_t group, int k, int gk, int t_eff) {
       int* dst = idx_ring + (gk % IDX_RING) * T * BLOCK_M;
       // lanes 0-15 fetch tile t, lanes 16-31 tile t+1: the warp's 16 rows of each
-      for (int t = lane >> 4; t < t_eff; t += 2) {
-        const int64_t row = (group * T + t) * BLOCK_M + warp * ROWS_PER_WARP + (lane & 15);
-        int* d = dst + t * BLOCK_M + warp * ROWS_PER_WARP + (lane & 15);
+      for (int t = lane / ROWS_PER_WARP; t < t_eff; t += TILES_PER_IDX_STEP) {
+        const int64_t row = (group * T + t) * BLOCK_M + warp * ROWS_PER_WARP + (lane % ROWS_PER_WARP);
+        int* d = dst + t * BLOCK_M + warp * ROWS_PER_WARP + (lane % ROWS_PER_WARP);
         if (row < p.n_out) {
           if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
           else *d = (int)row;
@@ -499,7 +503,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 // Missing neighbours (-1) must not reach the TMA — its out-of-range zero fill is 4.5x slower than a fetch, and one
 // shared dummy row hot-spots an L2 slice — so the issuing lane substitutes its own output row index (valid, distinct
 // per lane, L2-friendly) and flags the row in a byte mask; the convert warps write zeros for flagged rows.
-constexpr int TMA_WARP0 = LOAD_WARP + 1;                  // 14
+constexpr int CV_WARPS = 8;                               // convert warps 0-7
+constexpr int T_MMA_WARP = CV_WARPS + NUM_EPI_WARPS;      // 12 (epilogue = warps 8-11)
+constexpr int T_LOAD_WARP = T_MMA_WARP + 1;               // 13
+constexpr int TMA_WARP0 = T_LOAD_WARP + 1;                // 14
 constexpr int MAX_TMA_WARPS = 8;
 constexpr int MAX_RAW_SLOTS = 16;
 constexpr int IDX_DEPTH = 2;                              // neighbour-index ring entries per issue warp (all smem allows)
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == T_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_co
   pl.a_stage_bytes = a_stage_bytes; pl.b_stage_bytes = b_stage_bytes; pl.b_tile = b_tile;
   pl.KB = KB; pl.T = T; pl.acc_cols = acc_cols; pl.num_tiles = num_tiles; pl.num_groups = num_groups;
 
-  if (warp >= TMA_WARP0 || warp < NUM_GATHER_WARPS) {
+  if (warp >= TMA_WARP0 || warp < CV_WARPS) {
     // ============================ TMA issue (warps 14-21) and convert (warps 0-7) pairs ============================
     // Pair tw owns the sub-stages m = tw + NW*i.  NW is a multiple of H, so the pair always works on quarter
     // h = tw % H of the A stages n = tw / H + (NW / H) * i: the cursor below walks A stages.
@@ -743,16 +750,16 @@ __global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_co
         next_slot();
       }
     }
-  } else if (warp == LOAD_WARP) {
+  } else if (warp == T_LOAD_WARP) {
     if (lane == 0) role_weight_loader(p, pl);
-  } else if (warp == MMA_WARP) {
+  } else if (warp == T_MMA_WARP) {
     if (lane == 0) role_mma<NSPLIT>(p, pl);
   } else {
-    role_epilogue(p, pl, warp - NUM_GATHER_WARPS, lane);
+    role_epilogue(p, pl, warp - CV_WARPS, lane);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == T_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
