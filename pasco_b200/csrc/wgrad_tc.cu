@@ -38,7 +38,6 @@ struct WgradParams {
   int K, Cin, Cout, in_act;
   int stages, tmem_cols;
   int units_per_pass, num_units, num_subs, passes, ctas_per_pass;
-  int dbg;   // PASCO_WGRAD_DEBUG: bit0 = skip MMA issue, bit1 = gather nothing (timing experiments only)
 };
 
 constexpr int IDX_RING = 16;   // unit slots are short: fetch neighbour indices 15 slots ahead (HBM-latency bound otherwise)
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         const int k = desc[j * 8 + 3 + h];
         int* d = idx_ring + ((g & (IDX_RING - 1)) * 2 + h) * WG_R + warp * WROWS + (lane & 7);
         const int64_t row = rt * WG_R + warp * WROWS + (lane & 7);
-        if (p.nbr && k >= 0 && rt < num_rt && row < p.n_out && !(p.dbg & 16)) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
+        if (p.nbr && k >= 0 && rt < num_rt && row < p.n_out) cp_async4(smem_u32(d), p.nbr + (int64_t)k * p.n_out + row);
         else *d = (k >= 0 && rt < num_rt && row < p.n_out) ? (int)row : -1;
       }
       cp_async_commit();
@@ -204,7 +203,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
       const int64_t row = rt * WG_R + my_r;
       if (dj[0] == 0) {                                            // gout slot: identity rows
         int gidx = row < p.n_out ? (int)row : -1;
-        if (p.dbg & 2) gidx = -1;
         sub_load(r[0], p.gout, (int)p.gout_pitch, dj[1], gidx, lane);
         if (dj[2] >= 0) sub_load(r[1], p.gout, (int)p.gout_pitch, dj[2], gidx, lane);
       } else {
@@ -212,7 +210,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
         for (int h = 0; h < 2; ++h) {
           int idx = idx_ring[((g & (IDX_RING - 1)) * 2 + h) * WG_R + my_r];
           if (!p.nbr && idx >= 0) idx = (int)row;
-          if (p.dbg & 2) idx = -1;
           sub_load(r[h], p.in, (int)p.in_pitch, dj[1 + h], idx, lane);
         }
       }
@@ -239,13 +236,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
       } else {
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
         uint8_t* a = a_smem + (size_t)stage * a_bytes;
-        if (!(p.dbg & 8)) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, dj[1 + h], warp, lane,
-                                    p.in_scale, p.in_shift, p.in_act);
-        }
-        if (!(p.dbg & 32)) fence_proxy_async_smem();
+        for (int h = 0; h < 2; ++h)
+          sub_store<NSPLIT, true>(r[h], a + (size_t)h * WG_SUB_BYTES, a + (size_t)(2 + h) * WG_SUB_BYTES, dj[1 + h], warp, lane,
+                                  p.in_scale, p.in_shift, p.in_act);
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(full_bar + stage));
         if (++stage == p.stages) {
@@ -312,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
           float v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (ok && !(p.dbg & 4)) {
+          if (ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
           }
@@ -343,7 +338,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
             const uint32_t acc = (git > 0 || j > 0) ? 1u : 0u;
             const uint64_t da_hi = make_desc_sw128(a_hi + j * 2048, WG_SUB_BYTES, 1024);
             const uint64_t db_hi = make_desc_sw128(g_hi + j * 2048, WG_SUB_BYTES, 1024);
-            if (p.dbg & 1) continue;
             mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
             if (NSPLIT == 3) {
               const uint64_t da_lo = make_desc_sw128(a_lo + j * 2048, WG_SUB_BYTES, 1024);
@@ -404,10 +398,6 @@ extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t*
   p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
   p.gout_pitch = gout_pitch > 0 ? gout_pitch : Cout;
   p.stages = stages;
-  {
-    const char* d = getenv("PASCO_WGRAD_DEBUG");
-    p.dbg = d ? atoi(d) : 0;
-  }
   p.num_subs = K * (Cin / 64);
   p.num_units = (p.num_subs + 1) / 2;
   p.units_per_pass = 512 / Cout;
