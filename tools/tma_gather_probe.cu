@@ -1,6 +1,7 @@
 // Probe of the sm_100 TMA row gather (cp.async.bulk.tensor.2d.tile::gather4): (1) which tensor-map box makes it work and
 // what lands in shared memory (swizzle, out-of-range rows), (2) its throughput for 128-byte rows from an L2-sized table.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/tma_probe tools/tma_gather_probe.cu && gpurun_out/tma_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/tma_probe tools/tma_gather_probe.cu && /tmp/tma_probe
+// (profiles/r01_tma_gather_probe.txt is the output on the round-1 B200)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -188,8 +189,38 @@ int main() {
     printf("%-34s %d issuing warps/SM: %.3f ms, %.1f GB/s aggregate, %.1f B/clk/SM @1.9GHz, %.1f ns per gather4 per SM\n", what, nw, ms,
            bytes / ms / 1e6, bytes / ms / 1e6 / 148 / 1.9, ms * 1e6 / (iters * nw * 32.0));
   };
+  printf("-- (2) streaming, 512-B gather4 (bf16 rows of 64 ch, SWIZZLE_128B), 2-stage ring per warp\n");
   fill(10, -1, false);
+  run(k_stream<1>, 1, "random rows, 10% missing(-1)");
+  run(k_stream<2>, 2, "random rows, 10% missing(-1)");
+  run(k_stream<4>, 4, "random rows, 10% missing(-1)");
   run(k_stream<6>, 6, "random rows, 10% missing(-1)");
+  printf("-- out-of-range rows are zero-filled by the TMA: cost\n");
+  fill(65, -1, false);
+  run(k_stream<6>, 6, "random rows, 65% missing(-1)");
+  fill(90, -1, false);
+  run(k_stream<6>, 6, "random rows, 90% missing(-1)");
+  fill(90, (int)N + 5, false);
+  run(k_stream<6>, 6, "random rows, 90% missing(N+5)");
+  fill(100, -1, false);
+  run(k_stream<6>, 6, "all missing(-1)");
+  printf("-- missing neighbours redirected to real zero rows instead\n");
+  fill(65, (int)N - 1, false);
+  run(k_stream<6>, 6, "random, 65% -> ONE real zero row");
+  fill(100, (int)N - 1, false);
+  run(k_stream<6>, 6, "all -> ONE real row");
+  {
+    std::vector<int> hidx((size_t)n_tiles * 128);
+    uint64_t s = 88172645463325252ull;
+    for (size_t i = 0; i < hidx.size(); ++i) {
+      s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+      hidx[i] = ((int)(s % 100) < 90) ? (int)(N - 1 - (i % 128)) : (int)((s >> 8) % N);
+    }
+    CK(cudaMemcpy(d_idx, hidx.data(), hidx.size() * 4, cudaMemcpyHostToDevice));
+    run(k_stream<6>, 6, "random, 90% -> 128 zero rows");
+  }
+  fill(0, -1, true);
+  run(k_stream<6>, 6, "ascending nearby rows, 0% missing");
   auto run2 = [&](auto kern, int nw, int lanes, int g4b, const CUtensorMap& tmx) {
     const int smem = nw * lanes * g4b + 1024;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -205,8 +236,17 @@ int main() {
     printf("issue->wait loop, %2d warps x %2d lanes: %.3f ms, %.1f ns per gather4 per SM, %.1f GB/s aggregate, %.2f us per warp round\n", nw,
            lanes, ms, ms * 1e6 / n4, n4 * g4b * 148 / ms / 1e6, ms * 1e3 / iters);
   };
+  printf("-- (3) issue scaling, 512-B gather4: every warp issues `lanes` gather4s, waits for them, repeats\n");
+  fill(10, -1, false);
+  run2(k_issue<1, 32>, 1, 32, 512, tm_hi);
+  run2(k_issue<1, 16>, 1, 16, 512, tm_hi);
+  run2(k_issue<1, 8>, 1, 8, 512, tm_hi);
+  run2(k_issue<1, 1>, 1, 1, 512, tm_hi);
   run2(k_issue<4, 32>, 4, 32, 512, tm_hi);
   run2(k_issue<8, 32>, 8, 32, 512, tm_hi);
+  run2(k_issue<12, 32>, 12, 32, 512, tm_hi);
+  run2(k_issue<16, 16>, 16, 16, 512, tm_hi);
+  run2(k_issue<24, 8>, 24, 8, 512, tm_hi);
   // fp32 rows of 64 channels (256 B), no swizzle: 1 KB per gather4
   float* d_f32; CK(cudaMalloc(&d_f32, (size_t)N * 64 * 4)); CK(cudaMemset(d_f32, 0, (size_t)N * 64 * 4));
   CUtensorMap tm_f32;
@@ -217,10 +257,9 @@ int main() {
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tm_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_f32, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    printf("fp32 map encode rc=%d\n", (int)r);
+    printf("-- (4) fp32 rows of 64 channels (256 B, no swizzle), 1 KB per gather4 (map encode rc=%d)\n", (int)r);
   }
   fill(0, -1, false);
-  printf("fp32 256-B rows, 1 KB per gather4:\n");
   run2(k_issue<1, 32, 1024>, 1, 32, 1024, tm_f32);
   run2(k_issue<2, 32, 1024>, 2, 32, 1024, tm_f32);
   run2(k_issue<4, 32, 1024>, 4, 32, 1024, tm_f32);
