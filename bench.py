@@ -31,6 +31,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # scene sizes vary step to step
 import faulthandler  # noqa: E402
 
 import torch  # noqa: E402
@@ -182,7 +183,9 @@ def run_ours(a):
         log(f"SyncBatchNorm on {n_sync} fused BN layers")
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4, fused=True)
-    n_pool = min(a.pool, a.steps + a.warmup)
+    # every scene of the pool is seen by a warm-up step, so that the caching allocator holds blocks of every size before
+    # the timed regions (a first-touch cudaMalloc synchronises the device)
+    n_pool = max(1, min(a.pool, a.warmup))
     host_scenes = [pin(make_scene(GRID, OCC, 1, IN_CH, N_CLASSES, seed=sd)) for sd in parallel.scene_seeds(rank, world, n_pool)]
     dev_scenes = [to_device(s, dev) for s in host_scenes]
     torch.cuda.synchronize()

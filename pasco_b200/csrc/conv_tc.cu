@@ -54,6 +54,7 @@ struct ConvParams {
   const float* in_scale;
   const float* in_shift;
   float* out;
+  double* stats;       // optional [2*Cout]: column sums / sums of squares of `out` accumulate here (fused BN statistics)
   int64_t n_out;
   int64_t out_pitch;   // row stride of out (floats)
   int64_t in_pitch;    // row stride of in (floats)
@@ -135,6 +136,7 @@ struct Pipe {
   uint8_t* b_smem;          // [sb][B_hi | B_lo]
   uint64_t *afull, *aempty, *bfull, *bempty, *tfull, *tempty;
   uint32_t tmem_base;
+  double* stat_acc;         // [2*Cout] per-CTA accumulators in shared memory (nullptr: no fused statistics)
   int a_stage_bytes, b_stage_bytes, b_tile;
   int KB, T, acc_cols;
   int64_t num_tiles, num_groups;
@@ -213,9 +215,28 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
   }
 }
 
-// one warp per TMEM lane quadrant q: tcgen05.ld the accumulators (lane = output row), add bias, store fp32 rows
+// Column sums over the 32 rows held by a warp (lane = row, v[j] = column j): butterfly transpose-reduce, 31 shuffles;
+// lane j returns Σ_rows v[j].  Destroys v.
+__device__ __forceinline__ float warp_col_sums32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? v[i] : v[i + w];
+      const float keep = up ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+// one warp per TMEM lane quadrant q: tcgen05.ld the accumulators (lane = output row), add bias, store fp32 rows;
+// optionally accumulate the per-channel sum and sum of squares of what was stored (the BatchNorm statistics of the
+// next layer) — per warp in fp32 over its 32 rows, then in fp64 in shared memory, one global fp64 atomic per CTA.
 __device__ __forceinline__ void role_epilogue(const ConvParams& p, const Pipe& pl, int q, int lane) {
   int it = 0;
+  const bool want_stats = pl.stat_acc != nullptr;
   for (int64_t group = blockIdx.x; group < pl.num_groups; group += gridDim.x, ++it) {
     const int buf = it & 1;
     const int64_t rem = pl.num_tiles - group * pl.T;
@@ -226,36 +247,48 @@ __device__ __forceinline__ void role_epilogue(const ConvParams& p, const Pipe& p
       const int64_t row = (group * pl.T + t) * BLOCK_M + q * 32 + lane;
       const uint32_t taddr = pl.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * pl.acc_cols + t * p.Cout);
       float* orow = p.out + row * p.out_pitch;
-      int c0 = 0;
-      for (; c0 + 32 <= p.Cout; c0 += 32) {
+      const bool live = row < p.n_out;
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        const bool full = c0 + 32 <= p.Cout;          // else a 16-column tail (Cout % 32 == 16)
         float v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        if (row < p.n_out) {
+        if (full) {
+          tmem_ld32(taddr + c0, v);
+        } else {
+          float u[16];
+          tmem_ld16(taddr + c0, u);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          for (int j = 0; j < 16; ++j) {
+            v[j] = u[j];
+            v[j + 16] = 0.f;
           }
         }
-      }
-      if (c0 < p.Cout) {  // 16-column tail (Cout % 32 == 16)
-        float v[16];
-        tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
-        if (row < p.n_out) {
+        if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          for (int j = 0; j < 32; j += 4) {
+            if (full || j < 16) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (full || j < 16) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (want_stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = live ? v[j] : 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          const float s1 = warp_col_sums32(v, lane);
+          const float s2 = warp_col_sums32(sq, lane);
+          if (c0 + lane < p.Cout) {
+            atomicAdd(pl.stat_acc + c0 + lane, (double)s1);
+            atomicAdd(pl.stat_acc + p.Cout + c0 + lane, (double)s2);
           }
         }
       }
@@ -263,6 +296,10 @@ __device__ __forceinline__ void role_epilogue(const ConvParams& p, const Pipe& p
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(pl.tempty + buf));
+  }
+  if (want_stats) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps
+    for (int i = q * 32 + lane; i < 2 * p.Cout; i += NUM_EPI_WARPS * 32) atomicAdd(p.stats + i, pl.stat_acc[i]);
   }
 }
 
@@ -286,6 +323,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
   uint64_t* tfull = bars + 4 * MAX_STAGES;        // [2]
   uint64_t* tempty = bars + 4 * MAX_STAGES + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
+  double* stat_acc = p.stats ? reinterpret_cast<double*>(tmem_slot + 4) : nullptr;   // [2*Cout]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.Cin / KBLK;
@@ -293,6 +331,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
   const int64_t num_groups = (num_tiles + T - 1) / T;
   const int acc_cols = T * p.Cout;                // TMEM columns of one accumulator set
 
+  if (stat_acc)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += NUM_THREADS) stat_acc[i] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(smem_u32(afull + s), NUM_GATHER_WARPS);
@@ -315,6 +355,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
   pl.a_smem = a_smem; pl.b_smem = b_smem;
   pl.afull = afull; pl.aempty = aempty; pl.bfull = bfull; pl.bempty = bempty; pl.tfull = tfull; pl.tempty = tempty;
   pl.tmem_base = tmem_base;
+  pl.stat_acc = stat_acc;
   pl.a_stage_bytes = a_stage_bytes; pl.b_stage_bytes = b_stage_bytes; pl.b_tile = b_tile;
   pl.KB = KB; pl.T = T; pl.acc_cols = acc_cols; pl.num_tiles = num_tiles; pl.num_groups = num_groups;
 
@@ -580,6 +621,7 @@ __global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_co
   pl.a_smem = a_smem; pl.b_smem = b_smem;
   pl.afull = afull; pl.aempty = aempty; pl.bfull = bfull; pl.bempty = bempty; pl.tfull = tfull; pl.tempty = tempty;
   pl.tmem_base = tmem_base;
+  pl.stat_acc = nullptr;
   pl.a_stage_bytes = a_stage_bytes; pl.b_stage_bytes = b_stage_bytes; pl.b_tile = b_tile;
   pl.KB = KB; pl.T = T; pl.acc_cols = acc_cols; pl.num_tiles = num_tiles; pl.num_groups = num_groups;
 
@@ -810,7 +852,6 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_tc: Cin (%d) must be a multiple of 64", Cin);
   PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_tc: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
   PASCO_CHECK_ARG(K >= 1 && K <= 1024, "pasco_conv_forward_tc: K (%d) out of range", K);
-  PASCO_CHECK_ARG(stats == nullptr, "pasco_conv_forward_tc: fused output statistics are not implemented yet");
   PASCO_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)packed_w) & 15) == 0, "pasco_conv_forward_tc: pointers must be 16-byte aligned");
   if (n_out == 0) return 0;
   int dev = 0, smem_optin = 0;
@@ -824,7 +865,7 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   if (T > 4) T = 4;
   while (T > 1 && tiles < (int64_t)T * num_sms()) T >>= 1;   // small inputs: spread tiles over more SMs instead
   const int idx_bytes = IDX_RING * T * BLOCK_M * 4;
-  const int fixed = 1024 /*align slack*/ + idx_bytes + (4 * MAX_STAGES + 4) * 8 + 16;
+  const int fixed = 1024 /*align slack*/ + idx_bytes + (4 * MAX_STAGES + 4) * 8 + 16 + (stats ? 2 * Cout * 8 : 0);
   int sb = 2;
   int sa = (smem_optin - fixed - sb * b_stage) / a_stage;
   if (sa > 5) {  // room to spare: deepen the weight ring first
@@ -835,7 +876,7 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   PASCO_CHECK_ARG(sa >= 2, "pasco_conv_forward_tc: not enough shared memory (Cout=%d)", Cout);
   ConvParams p;
   p.in = in; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w; p.bias = bias;
-  p.in_scale = in_scale; p.in_shift = in_shift; p.out = out;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.out = out; p.stats = stats;
   p.n_out = n_out;
   p.out_pitch = out_pitch > 0 ? out_pitch : Cout;
   p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
@@ -858,7 +899,7 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   cudaError_t e;
   const bool prologue = in_scale != nullptr || in_act != 0;
   // ---- TMA-gather variant (k_conv_tma): Cout <= 128 leaves room for a raw fp32 ring next to the operand rings ----
-  if (conv_variant() && n_in >= 1 && ((p.in_pitch * 4) % 16) == 0) {
+  if (conv_variant() && stats == nullptr && n_in >= 1 && ((p.in_pitch * 4) % 16) == 0) {
     const int sa_t = 2, sb_t = 2;
     const int sub_rows = 32;      // 4 sub-stages per A tile: a convert warp then advances 2 A stages per step <= sa (phase rule)
     const int sub_bytes = sub_rows * KBLK * 4;

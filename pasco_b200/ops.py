@@ -22,6 +22,8 @@ def call(name, *args):
 _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
 _SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} forced onto the CUDA-core path
+_FUSE_BN_STATS = True    # forward convs leave their output's column statistics for the BatchNorm that follows
+_PENDING_STATS = None
 _USE_PLANES = False     # optional: forward / input-gradient convs gather pre-split bf16 planes with cp.async
                         # (conv_planes.cu; measured 1.16 vs 1.38 ms at C=64 incl. the split pass, slower at C>=128)
 PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
@@ -350,8 +352,11 @@ def _tc_ok(c_contract: int, c_out: int, K: int, kind: str = "fwd") -> bool:
 
 def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                transpose_w: bool, koff: Optional[Sequence[int]], bias: Optional[torch.Tensor] = None,
-               in_scale=None, in_shift=None, in_act: int = 0, packs: Optional[PackedWeights] = None) -> torch.Tensor:
-    """out[o] = Σ_k act(feats·scale+shift)[nbr[k,o]] @ Wk, Wk = W[koff[k]] (transposed when transpose_w)."""
+               in_scale=None, in_shift=None, in_act: int = 0, packs: Optional[PackedWeights] = None,
+               want_stats: bool = False) -> torch.Tensor:
+    """out[o] = Σ_k act(feats·scale+shift)[nbr[k,o]] @ Wk, Wk = W[koff[k]] (transposed when transpose_w).
+    want_stats: the kernel's epilogue also accumulates the column sums / sums of squares of `out` (the training-mode
+    BatchNorm statistics of the layer that follows) and leaves them for BatchNormAct (see take_pending_stats)."""
     K, Cin, Cout = weight.shape
     c_contract, c_out = (Cout, Cin) if transpose_w else (Cin, Cout)
     assert feats.shape[1] == c_contract
@@ -369,9 +374,14 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         call("pasco_conv_forward_planes", ptr(hi), ptr(lo), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(out), _PRECISION, 0)
     elif use_tc:
+        stats = None
+        if want_stats and _FUSE_BN_STATS and n_out >= 4096:
+            stats = torch.zeros(2, c_out, dtype=torch.float64, device=feats.device)
         call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
-             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act, None,
-             ptr(out), _PRECISION, 0, 0)
+             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act,
+             ptr(stats), ptr(out), _PRECISION, 0, 0)
+        global _PENDING_STATS
+        _PENDING_STATS = (out.data_ptr(), out._version, tuple(out.shape), stats) if stats is not None else None
     else:
         assert in_scale is None and in_act == 0, "fused prologue needs the tensor-core path"
         if nbr is None:
@@ -386,6 +396,21 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
                           pairs=PAIR_COUNTS.get(nbr.data_ptr()) if nbr is not None else None,
                           tc=use_tc, precision=_PRECISION)))
     return out
+
+
+def take_pending_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """Column statistics a convolution epilogue produced for exactly this tensor (same storage, shape and version —
+    any in-place change since bumps the version), or None.  Consumed once."""
+    global _PENDING_STATS
+    pend, _PENDING_STATS = _PENDING_STATS, None
+    if pend is not None and pend[0] == x.data_ptr() and pend[1] == x._version and pend[2] == tuple(x.shape):
+        return pend[3]
+    return None
+
+
+def fuse_bn_stats(flag: bool) -> None:
+    global _FUSE_BN_STATS
+    _FUSE_BN_STATS = bool(flag)
 
 
 def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor], K: int, Cin: int, Cout: int,
@@ -424,7 +449,7 @@ class SparseConv(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.save_for_backward(feats, weight)
         return conv_apply(feats, weight, kmap.nbr, kmap.n_out, False, None,
-                          bias.view(-1).contiguous() if bias is not None else None, packs=packs)
+                          bias.view(-1).contiguous() if bias is not None else None, packs=packs, want_stats=True)
 
     @staticmethod
     def backward(ctx, g):
@@ -519,7 +544,9 @@ class BatchNormAct(torch.autograd.Function):
         x = x.contiguous()
         n, c = x.shape
         dev = x.device
-        stats = column_stats(x)
+        stats = take_pending_stats(x)
+        if stats is None:
+            stats = column_stats(x)
         count_dev = None
         if group is not None:
             packed = torch.cat([stats.view(-1), torch.tensor([float(n)], dtype=torch.float64, device=dev)])

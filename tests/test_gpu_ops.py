@@ -281,6 +281,34 @@ def test_conv_tma_and_register_gather_are_bit_identical(prec):
     assert outs[0][0].abs().sum() > 0
 
 
+@pytest.mark.parametrize("cin,cout,bias", [(64, 64, False), (64, 128, True), (128, 256, False), (64, 48, True)])
+def test_conv_epilogue_statistics(cin, cout, bias):
+    """Fused BatchNorm statistics: the conv epilogue's column sums / sums of squares of its output (incl. bias, a ragged
+    last tile and the 16-column tail of Cout = 48) equal a separate pass over the stored output; they are handed to the
+    next BatchNormAct only for the untouched tensor."""
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(5)
+    occ = torch.rand(48, 40, 16, generator=g) < 0.3
+    c = torch.nonzero(occ).int()
+    C = torch.cat([torch.zeros(c.shape[0], 1, dtype=torch.int32), c], 1).cuda()
+    N = C.shape[0]
+    assert N >= 4096 and N % 128 != 0
+    table, _ = ops.hash_insert(C)
+    nbr = ops.kernel_map_probe(C, table, 3, (1, 1, 1))
+    F = torch.randn(N, cin, generator=g).cuda()
+    W = (torch.randn(27, cin, cout, generator=g) * 0.1).cuda()
+    b = torch.randn(cout, generator=g).cuda() if bias else None
+    out = ops.conv_apply(F, W, nbr, N, False, None, b, want_stats=True)
+    ref = ops.column_stats(out)
+    got = ops.take_pending_stats(out)
+    assert got is not None and ops.take_pending_stats(out) is None          # consumed once
+    assert relerr(got, ref) <= 1e-6
+    out2 = ops.conv_apply(F, W, nbr, N, False, None, b, want_stats=True)
+    out2.add_(1.0)                                                           # in-place change → statistics are stale
+    assert ops.take_pending_stats(out2) is None
+
+
 def test_conv_many_tiles_per_cta(ME):
     """~59k voxels: every persistent CTA walks several 128-row tiles (and several 64-row wgrad tiles
     accumulating in TMEM), unlike the small cases above."""
