@@ -140,6 +140,18 @@ int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int
                           const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
                           double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
                           pasco_stream_t s);
+/* Split-K form of the same convolution for shapes with few output tiles and many offsets (the dense bottleneck of
+ * layers.py:646-726 runs as 32 tiles x 245 offsets: one CTA per tile would leave 116 of 148 SMs idle).  The offsets are
+ * cut into ranges, every (tile, range) pair is a work item whose partial result goes to the caller's workspace, and a
+ * second kernel adds the partials in a fixed order (+ bias) — still deterministic, no atomics.
+ * pasco_conv_splitk_workspace_bytes returns 0 when the shape is not worth splitting (then call pasco_conv_forward_tc). */
+int64_t pasco_conv_splitk_workspace_bytes(int32_t K, int64_t n_out, int32_t Cout);
+int pasco_conv_forward_splitk(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out, int32_t Cin,
+                              int32_t Cout, const void* packed_w, const int32_t* koff_map, const float* bias,
+                              const float* in_scale, const float* in_shift, int32_t in_act, float* out, int32_t precision,
+                              int64_t in_pitch, int64_t out_pitch, void* workspace, int64_t workspace_bytes,
+                              pasco_stream_t s);
+
 /* Two kernels implement pasco_conv_forward_tc: the register-gather kernel (variant 0, default) and a TMA-gather kernel
  * (variant 1: tile::gather4 fetches the neighbour rows into a raw shared-memory ring, warps only convert; used when
  * Cout <= 128 leaves room for that ring, otherwise variant 0 runs).  Results are identical bit for bit (same operand

@@ -61,6 +61,8 @@ struct ConvParams {
   int K, Cin, Cout, in_act;
   int sa, sb, tiles_per_group, tmem_cols;
   int koff_base, koff_step;   // weight slice of table row k = koff_base + koff_step * k
+  int ksplit, kchunk;         // split-K: work item v = (tile group v / ksplit, offsets [ks*kchunk, (ks+1)*kchunk)), partial
+                              // results go to out + ks * n_out * out_pitch (summed by k_splitk_reduce)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -121,9 +123,10 @@ constexpr int IDX_RING = 6;  // neighbour-index ring depth (entries of T*128 int
 
 // position of a gather warp inside the flat slot sequence  group → k → kb → t
 struct SlotIt {
-  int64_t group;   // tile group handled by this CTA
-  int gk;          // running (group, k) counter → index ring slot
-  int k, kb, t;
+  int64_t v;       // work item handled by this CTA: tile group v / ksplit, offset range number v % ksplit
+  int64_t group;   // = v / ksplit
+  int gk;          // running (work item, k) counter → index ring slot
+  int k, k1, kb, t;  // k walks [k0(v), k1(v))
   int t_eff;       // tiles in this group
   bool valid;
 };
@@ -147,8 +150,9 @@ __device__ __forceinline__ void role_weight_loader(const ConvParams& p, const Pi
   int stage = 0;
   uint32_t phase = 0;
   const uint32_t bytes = (uint32_t)pl.b_stage_bytes;
-  for (int64_t group = blockIdx.x; group < pl.num_groups; group += gridDim.x) {
-    for (int k = 0; k < p.K; ++k) {
+  for (int64_t v = blockIdx.x; v < pl.num_groups * p.ksplit; v += gridDim.x) {
+    const int k0 = (int)(v % p.ksplit) * p.kchunk, k1 = k0 + p.kchunk < p.K ? k0 + p.kchunk : p.K;
+    for (int k = k0; k < k1; ++k) {
       for (int kb = 0; kb < pl.KB; ++kb) {
         mbar_wait(smem_u32(pl.bempty + stage), phase ^ 1);
         mbar_arrive_expect_tx(smem_u32(pl.bfull + stage), bytes);
@@ -170,13 +174,15 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;
   int it = 0;
-  for (int64_t group = blockIdx.x; group < pl.num_groups; group += gridDim.x, ++it) {
+  for (int64_t v = blockIdx.x; v < pl.num_groups * p.ksplit; v += gridDim.x, ++it) {
     const int buf = it & 1;
+    const int64_t group = v / p.ksplit;
+    const int k0 = (int)(v % p.ksplit) * p.kchunk, k1 = k0 + p.kchunk < p.K ? k0 + p.kchunk : p.K;
     const int64_t rem = pl.num_tiles - group * pl.T;
     const int t_eff = rem < pl.T ? (int)rem : pl.T;
     mbar_wait(smem_u32(pl.tempty + buf), ((it >> 1) & 1) ^ 1);
     tc_fence_after();
-    for (int k = 0; k < p.K; ++k) {
+    for (int k = k0; k < k1; ++k) {
       for (int kb = 0; kb < pl.KB; ++kb) {
         mbar_wait(smem_u32(pl.bfull + sb), pb);
         const uint32_t b_hi = smem_u32(pl.b_smem + (size_t)sb * pl.b_stage_bytes), b_lo = b_hi + pl.b_tile;
@@ -187,7 +193,7 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
           const uint32_t d_tmem = pl.tmem_base + (uint32_t)(buf * pl.acc_cols + t * p.Cout);
 #pragma unroll
           for (int j = 0; j < KBLK / 16; ++j) {
-            const uint32_t accum = (k > 0 || kb > 0 || j > 0) ? 1u : 0u;
+            const uint32_t accum = (k > k0 || kb > 0 || j > 0) ? 1u : 0u;
             const uint64_t da_hi = make_desc_sw128(a_hi + j * 32, 16, 1024);
             const uint64_t db_hi = make_desc_sw128(b_hi + j * 32, 16, 1024);
             mma_bf16(d_tmem, da_hi, db_hi, idesc, accum);
@@ -237,8 +243,10 @@ __device__ __forceinline__ float warp_col_sums32(float (&v)[32], int lane) {
 __device__ __forceinline__ void role_epilogue(const ConvParams& p, const Pipe& pl, int q, int lane) {
   int it = 0;
   const bool want_stats = pl.stat_acc != nullptr;
-  for (int64_t group = blockIdx.x; group < pl.num_groups; group += gridDim.x, ++it) {
+  for (int64_t v = blockIdx.x; v < pl.num_groups * p.ksplit; v += gridDim.x, ++it) {
     const int buf = it & 1;
+    const int64_t group = v / p.ksplit;
+    float* out_part = p.out + (v % p.ksplit) * p.n_out * p.out_pitch;    // this split's partial output
     const int64_t rem = pl.num_tiles - group * pl.T;
     const int t_eff = rem < pl.T ? (int)rem : pl.T;
     mbar_wait(smem_u32(pl.tfull + buf), (it >> 1) & 1);
@@ -246,7 +254,7 @@ __device__ __forceinline__ void role_epilogue(const ConvParams& p, const Pipe& p
     for (int t = 0; t < t_eff; ++t) {
       const int64_t row = (group * pl.T + t) * BLOCK_M + q * 32 + lane;
       const uint32_t taddr = pl.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * pl.acc_cols + t * p.Cout);
-      float* orow = p.out + row * p.out_pitch;
+      float* orow = out_part + row * p.out_pitch;
       const bool live = row < p.n_out;
       for (int c0 = 0; c0 < p.Cout; c0 += 32) {
         const bool full = c0 + 32 <= p.Cout;          // else a 16-column tail (Cout % 32 == 16)
@@ -382,31 +390,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
       }
       cp_async_commit();
     };
+    const int64_t num_items = num_groups * p.ksplit;
+    // position `it` at the first offset of work item v
+    auto enter = [&](SlotIt& it, int64_t v) {
+      it.v = v;
+      it.valid = v < num_items;
+      if (it.valid) {
+        it.group = v / p.ksplit;
+        it.k = (int)(v % p.ksplit) * p.kchunk;
+        it.k1 = it.k + p.kchunk < p.K ? it.k + p.kchunk : p.K;
+        const int64_t rem = num_tiles - it.group * T;
+        it.t_eff = rem < T ? (int)rem : T;
+      }
+    };
     auto advance = [&](SlotIt& it) {
       if (++it.t < it.t_eff) return;
       it.t = 0;
       if (++it.kb < KB) return;
       it.kb = 0;
       ++it.gk;
-      if (++it.k < p.K) return;
-      it.k = 0;
-      it.group += gridDim.x;
-      it.valid = it.group < num_groups;
-      if (it.valid) {
-        int64_t rem = num_tiles - it.group * T;
-        it.t_eff = rem < T ? (int)rem : T;
-      }
+      if (++it.k < it.k1) return;
+      enter(it, it.v + gridDim.x);
     };
-    // the (group,k) pair that follows `it`'s by `ahead` steps, for index prefetch
+    // the (work item, k) pair that follows `it`'s by `ahead` steps, for index prefetch
     auto prefetch_ahead = [&](const SlotIt& it, int ahead) {
-      int64_t g = it.group;
-      int k = it.k + ahead, gk = it.gk + ahead;
-      while (k >= p.K) {
-        k -= p.K;
-        g += gridDim.x;
+      int64_t v = it.v;
+      int k = it.k + ahead, k1 = it.k1;
+      const int gk = it.gk + ahead;
+      while (v < num_items && k >= k1) {
+        const int over = k - k1;
+        v += gridDim.x;
+        if (v >= num_items) break;
+        const int k0 = (int)(v % p.ksplit) * p.kchunk;
+        k1 = k0 + p.kchunk < p.K ? k0 + p.kchunk : p.K;
+        k = k0 + over;
       }
-      if (g < num_groups) {
-        int64_t rem = num_tiles - g * T;
+      if (v < num_items) {
+        const int64_t g = v / p.ksplit;
+        const int64_t rem = num_tiles - g * T;
         prefetch_idx(g, k, gk, rem < T ? (int)rem : T);
       } else {
         cp_async_commit();  // keep the group count uniform
@@ -414,11 +435,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     };
 
     SlotIt ld;
-    ld.group = blockIdx.x; ld.gk = 0; ld.k = 0; ld.kb = 0; ld.t = 0;
-    ld.valid = ld.group < num_groups;
+    ld.gk = 0; ld.kb = 0; ld.t = 0; ld.group = 0; ld.k = 0; ld.k1 = 0; ld.t_eff = 0;
+    enter(ld, blockIdx.x);
     if (ld.valid) {
-      int64_t rem = num_tiles - ld.group * T;
-      ld.t_eff = rem < T ? (int)rem : T;
       // prime the index ring: entries 0 .. IDX_RING-2
       for (int a = 0; a < IDX_RING - 1; ++a) prefetch_ahead(ld, a);
     }
@@ -843,11 +862,40 @@ extern "C" int pasco_conv_pack_weights(const float* W, int32_t K, int32_t Cin, i
   return 0;
 }
 
-extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
+namespace {
+
+// split-K plan: few output tiles and many offsets (the dense bottleneck: 32 tiles x 245 offsets) leave most SMs idle with
+// one CTA per tile; cut the offsets into `ksplit` ranges so that ~2 x #SM work items exist.  1 = no split.
+int splitk_plan(int K, int64_t n_out) {
+  const int64_t tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
+  if (K < 18 || tiles * 2 > num_sms()) return 1;
+  int ks = (int)((2 * (int64_t)num_sms() + tiles - 1) / tiles);
+  if (ks > K / 6) ks = K / 6;                       // at least 6 offsets per work item
+  return ks < 2 ? 1 : ks;
+}
+
+// out[r, :] = bias + Σ_s part[s, r, :]   (deterministic reduction of the split-K partial outputs)
+__global__ void k_splitk_reduce(const float* __restrict__ part, int ksplit, int64_t n, int C, const float* __restrict__ bias,
+                                float* __restrict__ out, int64_t out_pitch) {
+  const int cv = C >> 2;
+  const int64_t total = n * cv;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / cv;
+    const int c = (int)(t - r * cv) << 2;
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + ((int64_t)s * n + r) * C + c));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + r * out_pitch + c) = acc;
+  }
+}
+
+int conv_forward_impl(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
                                      int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map,
                                      const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
                                      double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
-                                     pasco_stream_t s) {
+                                     int ksplit, float* workspace, pasco_stream_t s) {
   PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_forward_tc: precision must be 1 (bf16) or 3 (bf16x3)");
   PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_tc: Cin (%d) must be a multiple of 64", Cin);
   PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_tc: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
@@ -864,6 +912,7 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   if (T < 1) T = 1;
   if (T > 4) T = 4;
   while (T > 1 && tiles < (int64_t)T * num_sms()) T >>= 1;   // small inputs: spread tiles over more SMs instead
+  if (ksplit > 1) T = 1;
   const int idx_bytes = IDX_RING * T * BLOCK_M * 4;
   const int fixed = 1024 /*align slack*/ + idx_bytes + (4 * MAX_STAGES + 4) * 8 + 16 + (stats ? 2 * Cout * 8 : 0);
   int sb = 2;
@@ -879,6 +928,12 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
   p.in_scale = in_scale; p.in_shift = in_shift; p.out = out; p.stats = stats;
   p.n_out = n_out;
   p.out_pitch = out_pitch > 0 ? out_pitch : Cout;
+  p.ksplit = 1; p.kchunk = K;
+  if (ksplit > 1) {       // partial outputs [ksplit, n_out, Cout] into the workspace, bias added by the reduction
+    p.ksplit = ksplit; p.kchunk = (K + ksplit - 1) / ksplit;
+    p.ksplit = (K + p.kchunk - 1) / p.kchunk;       // no empty ranges
+    p.out = workspace; p.out_pitch = Cout; p.bias = nullptr; p.stats = nullptr;
+  }
   p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
   PASCO_CHECK_ARG(p.out_pitch % 4 == 0 && p.in_pitch % 4 == 0, "pasco_conv_forward_tc: pitches must be multiples of 4 floats");
   p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
@@ -894,12 +949,12 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
     if (!ident) { p.koff_base = K - 1; p.koff_step = -1; }
   }
   const size_t smem = (size_t)sa * a_stage + (size_t)sb * b_stage + fixed;
-  int64_t groups = (tiles + T - 1) / T;
+  int64_t groups = (tiles + T - 1) / T * p.ksplit;
   int grid = (int)(groups < num_sms() ? groups : num_sms());
   cudaError_t e;
   const bool prologue = in_scale != nullptr || in_act != 0;
   // ---- TMA-gather variant (k_conv_tma): Cout <= 128 leaves room for a raw fp32 ring next to the operand rings ----
-  if (conv_variant() && stats == nullptr && n_in >= 1 && ((p.in_pitch * 4) % 16) == 0) {
+  if (conv_variant() && stats == nullptr && ksplit <= 1 && n_in >= 1 && ((p.in_pitch * 4) % 16) == 0) {
     const int sa_t = 2, sb_t = 2;
     const int sub_rows = 32;      // 4 sub-stages per A tile: a convert warp then advances 2 A stages per step <= sa (phase rule)
     const int sub_bytes = sub_rows * KBLK * 4;
@@ -943,5 +998,40 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
     return -1;
   }
   PASCO_CHECK_LAUNCH("pasco_conv_forward_tc");
+  if (p.ksplit > 1) {
+    k_splitk_reduce<<<grid_for(n_out * (Cout / 4), 256), 256, 0, (cudaStream_t)s>>>(workspace, p.ksplit, n_out, Cout, bias, out,
+                                                                                out_pitch > 0 ? out_pitch : Cout);
+    PASCO_CHECK_LAUNCH("pasco_conv_forward_tc(split-K reduce)");
+  }
   return 0;
+}
+
+}  // namespace
+
+extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
+                                     int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map,
+                                     const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
+                                     double* stats, float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch,
+                                     pasco_stream_t s) {
+  return conv_forward_impl(in, n_in, nbr, K, n_out, Cin, Cout, packed_w, koff_map, bias, in_scale, in_shift, in_act, stats, out,
+                           precision, in_pitch, out_pitch, 1, nullptr, s);
+}
+
+extern "C" int64_t pasco_conv_splitk_workspace_bytes(int32_t K, int64_t n_out, int32_t Cout) {
+  const int ks = splitk_plan(K, n_out);
+  return ks > 1 ? (int64_t)ks * n_out * Cout * 4 : 0;
+}
+
+extern "C" int pasco_conv_forward_splitk(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
+                                         int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map,
+                                         const float* bias, const float* in_scale, const float* in_shift, int32_t in_act,
+                                         float* out, int32_t precision, int64_t in_pitch, int64_t out_pitch, void* workspace,
+                                         int64_t workspace_bytes, pasco_stream_t s) {
+  const int ks = splitk_plan(K, n_out);
+  PASCO_CHECK_ARG(ks > 1, "pasco_conv_forward_splitk: this shape is not split (workspace_bytes = 0): call pasco_conv_forward_tc");
+  PASCO_CHECK_ARG(workspace != nullptr && workspace_bytes >= (int64_t)ks * n_out * Cout * 4,
+                  "pasco_conv_forward_splitk: workspace too small (%lld bytes)", (long long)workspace_bytes);
+  PASCO_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "pasco_conv_forward_splitk: workspace must be 16-byte aligned");
+  return conv_forward_impl(in, n_in, nbr, K, n_out, Cin, Cout, packed_w, koff_map, bias, in_scale, in_shift, in_act, nullptr, out,
+                           precision, in_pitch, out_pitch, ks, (float*)workspace, s);
 }

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import call as _raw_call, ptr, int_array
+from ._lib import call as _raw_call, ptr, int_array, load
 
 
 def call(name, *args):
@@ -22,6 +22,7 @@ def call(name, *args):
 _PRECISION = 3          # 3 = bf16x3 split ("fp32" parity mode), 1 = plain bf16 operands
 _FORCE_SIMT = False     # validation switch: run every conv on the CUDA-core path
 _SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} forced onto the CUDA-core path
+_SPLIT_K = True          # few-tile / many-offset convs (dense bottleneck) are split over the offsets
 _FUSE_BN_STATS = True    # forward convs leave their output's column statistics for the BatchNorm that follows
 _PENDING_STATS = None
 _USE_PLANES = False     # optional: forward / input-gradient convs gather pre-split bf16 planes with cp.async
@@ -321,7 +322,6 @@ class PackedWeights:
 
 def set_conv_variant(variant: int) -> None:
     """0 (default) = register-gather conv kernel, 1 = TMA-gather kernel where eligible (Cout <= 128)."""
-    from ._lib import load
     if load().pasco_conv_set_variant(int(variant)) != 0:
         raise RuntimeError(load().pasco_last_error().decode())
 
@@ -373,6 +373,11 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         hi, lo = split_planes(feats, in_scale, in_shift, in_act)
         call("pasco_conv_forward_planes", ptr(hi), ptr(lo), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(out), _PRECISION, 0)
+    elif use_tc and _SPLIT_K and (ws_bytes := load().pasco_conv_splitk_workspace_bytes(kk, n_out, c_out)) > 0:
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=feats.device)
+        call("pasco_conv_forward_splitk", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
+             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act,
+             ptr(out), _PRECISION, 0, 0, ptr(ws), ws_bytes)
     elif use_tc:
         stats = None
         if want_stats and _FUSE_BN_STATS and n_out >= 4096:
@@ -406,6 +411,11 @@ def take_pending_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
     if pend is not None and pend[0] == x.data_ptr() and pend[1] == x._version and pend[2] == tuple(x.shape):
         return pend[3]
     return None
+
+
+def split_k(flag: bool) -> None:
+    global _SPLIT_K
+    _SPLIT_K = bool(flag)
 
 
 def fuse_bn_stats(flag: bool) -> None:

@@ -309,6 +309,49 @@ def test_conv_epilogue_statistics(cin, cout, bias):
     assert ops.take_pending_stats(out2) is None
 
 
+@pytest.mark.parametrize("kernel,cin,cout,bias", [((7, 7, 5), 64, 64, True), ((5, 5, 3), 128, 128, False), ((3, 3, 3), 64, 128, True)])
+def test_conv_split_k_matches_unsplit(kernel, cin, cout, bias):
+    """Few output tiles x many offsets (the dense-bottleneck shape) run as (tile, offset-range) work items with a
+    deterministic reduction; result = the one-CTA-per-tile kernel up to the fp32 accumulation order of K*Cin (up to 15,680)
+    products per output — both are compared with an fp64 evaluation of the same contraction, incl. mirrored offsets."""
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(11)
+    X, Y, Z = 16, 16, 4
+    grid = torch.stack(torch.meshgrid(torch.arange(X), torch.arange(Y), torch.arange(Z), indexing="ij"), -1).view(-1, 3)
+    C = torch.cat([torch.zeros(grid.shape[0], 1, dtype=torch.int64), grid], 1).int().cuda()
+    N = C.shape[0]
+    table, _ = ops.hash_insert(C)
+    nbr = ops.kernel_map_box(C, table, kernel, (1, 1, 1))
+    K = nbr.shape[0]
+    assert ops.load().pasco_conv_splitk_workspace_bytes(K, N, cout) > 0
+    F = torch.randn(N, cin, generator=g).cuda()
+    W = (torch.randn(K, cin, cout, generator=g) * 0.05).cuda()
+    b = torch.randn(cout, generator=g).cuda() if bias else None
+    G = torch.randn(N, cout, generator=g).cuda()
+    koff = [K - 1 - k for k in range(K)]
+    outs = []
+    try:
+        for flag in (True, False):
+            ops.split_k(flag)
+            outs.append((ops.conv_apply(F, W, nbr, N, False, None, b), ops.conv_apply(G, W, nbr, N, True, koff)))
+    finally:
+        ops.split_k(True)
+    Fd, Gd, Wd = F.double(), G.double(), W.double()
+    ref_f = torch.zeros(N, cout, dtype=torch.float64, device="cuda") + (b.double() if bias else 0.0)
+    ref_g = torch.zeros(N, cin, dtype=torch.float64, device="cuda")
+    for k in range(K):
+        src = nbr[k].long()
+        ok = src >= 0
+        ref_f[ok] += Fd[src[ok]] @ Wd[k]
+        ref_g[ok] += Gd[src[ok]] @ Wd[koff[k]].t()
+    for o_f, o_g in outs:
+        assert relerr(o_f, ref_f) <= TOL_TIGHT and relerr(o_g, ref_g) <= TOL_TIGHT
+    assert relerr(outs[0][0], outs[1][0]) <= 2e-4 and relerr(outs[0][1], outs[1][1]) <= 2e-4
+    again = ops.conv_apply(F, W, nbr, N, False, None, b)
+    assert torch.equal(again, outs[0][0])                       # deterministic
+
+
 def test_conv_many_tiles_per_cta(ME):
     """~59k voxels: every persistent CTA walks several 128-row tiles (and several 64-row wgrad tiles
     accumulating in TMEM), unlike the small cases above."""
