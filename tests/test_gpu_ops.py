@@ -299,14 +299,18 @@ def test_conv_epilogue_statistics(cin, cout, bias):
     F = torch.randn(N, cin, generator=g).cuda()
     W = (torch.randn(27, cin, cout, generator=g) * 0.1).cuda()
     b = torch.randn(cout, generator=g).cuda() if bias else None
-    out = ops.conv_apply(F, W, nbr, N, False, None, b, want_stats=True)
-    ref = ops.column_stats(out)
-    got = ops.take_pending_stats(out)
-    assert got is not None and ops.take_pending_stats(out) is None          # consumed once
-    assert relerr(got, ref) <= 1e-6
-    out2 = ops.conv_apply(F, W, nbr, N, False, None, b, want_stats=True)
-    out2.add_(1.0)                                                           # in-place change → statistics are stale
-    assert ops.take_pending_stats(out2) is None
+    ops.split_k(False)            # 72 tiles x 27 offsets would otherwise take the split-K path (no fused statistics there)
+    try:
+        out = ops.conv_apply(F, W, nbr, N, False, None, b, want_stats=True)
+        ref = ops.column_stats(out)
+        got = ops.take_pending_stats(out)
+        assert got is not None and ops.take_pending_stats(out) is None          # consumed once
+        assert relerr(got, ref) <= 1e-6
+        out2 = ops.conv_apply(F, W, nbr, N, False, None, b, want_stats=True)
+        out2.add_(1.0)                                                           # in-place change → statistics are stale
+        assert ops.take_pending_stats(out2) is None
+    finally:
+        ops.split_k(True)
 
 
 @pytest.mark.parametrize("kernel,cin,cout,bias", [((7, 7, 5), 64, 64, True), ((5, 5, 3), 128, 128, False), ((3, 3, 3), 64, 128, True)])
