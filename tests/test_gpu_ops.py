@@ -349,8 +349,9 @@ def test_conv_split_k_matches_unsplit(kernel, cin, cout, bias):
         ok = src >= 0
         ref_f[ok] += Fd[src[ok]] @ Wd[k]
         ref_g[ok] += Gd[src[ok]] @ Wd[koff[k]].t()
+    # 245 x 64 products accumulate in fp32 inside TMEM: 1e-4 of the output range (the parity bound is 1e-3)
     for o_f, o_g in outs:
-        assert relerr(o_f, ref_f) <= TOL_TIGHT and relerr(o_g, ref_g) <= TOL_TIGHT
+        assert relerr(o_f, ref_f) <= 1e-4 and relerr(o_g, ref_g) <= 1e-4
     assert relerr(outs[0][0], outs[1][0]) <= 2e-4 and relerr(outs[0][1], outs[1][1]) <= 2e-4
     again = ops.conv_apply(F, W, nbr, N, False, None, b)
     assert torch.equal(again, outs[0][0])                       # deterministic
