@@ -21,6 +21,7 @@ cores on a bounded crop of the same workload (ME 0.5.4 itself is not installable
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -208,6 +209,14 @@ def run_ours(a):
     loss_host = torch.zeros(max(a.steps, 1), dtype=torch.float32).pin_memory()
 
     def timed(n_steps, from_host, profile_last=False):
+        gc.collect()
+        gc.disable()            # no collector pauses inside the timed region (collected between regions)
+        try:
+            return _timed(n_steps, from_host, profile_last)
+        finally:
+            gc.enable()
+
+    def _timed(n_steps, from_host, profile_last):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -251,6 +260,12 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), last
 
+    # map the allocator's address range once, outside the timed regions: the per-step working set (~20 GB, sizes differ
+    # from scene to scene) otherwise grows by cuMemMap calls whenever a step needs a block that is not cached yet
+    reserve = torch.empty(int(os.environ.get("PASCO_BENCH_RESERVE_GB", "40")) << 30, dtype=torch.uint8, device=dev)
+    del reserve
+    gc.collect()
+    gc.freeze()
     log(f"model + {n_pool} scenes ready")
     for i in range(a.warmup):
         faulthandler.dump_traceback_later(240, exit=False)
