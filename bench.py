@@ -264,6 +264,7 @@ def run_ours(a):
     # from scene to scene) otherwise grows by cuMemMap calls whenever a step needs a block that is not cached yet
     reserve = torch.empty(int(os.environ.get("PASCO_BENCH_RESERVE_GB", "40")) << 30, dtype=torch.uint8, device=dev)
     del reserve
+    torch.cuda.reset_peak_memory_stats(dev)
     gc.collect()
     gc.freeze()
     log(f"model + {n_pool} scenes ready")
