@@ -58,9 +58,12 @@ def _peaks():
     return 6650.0, 1400.0, "fallback"
 
 
-def _ncu_traffic(kind):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
-    capture of the same layer shape (profiles/r01_ncu_conv_v4.json: N=1.05 M rows, C=64, bf16x3); None if absent."""
+def _ncu_traffic(kind, meta):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) per launch of the dominant kernel from the committed
+    ncu --set full capture of the same layer shape (profiles/r01_ncu_conv_v4.json: N=1.05 M rows, C=64, bf16x3);
+    None if the dominant group is another shape or the capture is absent."""
+    if not (meta["Cin"] == 64 and meta["Cout"] == 64 and meta["K"] == 27 and 0.9e6 < meta["n_out"] < 1.2e6 and meta["precision"] == 3):
+        return None
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_conv_v4.json")))
         want = "k_wgrad_tc" if kind == "wgrad" else "k_conv_tc"
@@ -70,7 +73,7 @@ def _ncu_traffic(kind):
                 for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     v, u = k[key].split()
                     tot += float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[u]
-                return {"bytes_per_launch": tot, "source": "profiles/r01_ncu_conv_v4.json (C=64, N=1.05M rows)"}
+                return tot
     except Exception:
         pass
     return None
@@ -325,7 +328,9 @@ def run_ours(a):
         m = top["meta"]
         roof = {"kernel": f"k_conv_tc<{m['precision']}> {top['kind']} K={m['K']} {m['Cin']}->{m['Cout']} n_out~{m['n_out']}",
                 "bound": "tensor", "achieved": round(ach_tf, 2), "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": round(ach_tf / tf_peak, 4), "traffic": _ncu_traffic(top["kind"]), "peak_source": peak_src,
+                "frac": round(ach_tf / tf_peak, 4), "traffic": _ncu_traffic(top["kind"], m),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_conv_v4.json (same layer shape)",
+                "algorithmic_bytes_per_launch": round(top["bytes"] / top["n"]), "peak_source": peak_src,
                 "launch_ms": round(per_launch_ms, 4), "launches": top["n"],
                 "algorithmic": "flops = 2*pairs*Cin*Cout per launch (useful MACs; bf16x3 issues 3x that on the tensor pipe)",
                 "tensor_issued_TFLOPs": round(ach_tf * (3 if m["precision"] == 3 else 1), 2),
