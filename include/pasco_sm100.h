@@ -103,13 +103,15 @@ int pasco_gather_coords(const int32_t* src, const int32_t* rows, int64_t n_rows,
 
 /* ---- dense <-> sparse (SparseTensor.dense / ME.to_sparse: augmenter.py:15-22,
  *      unet3d_sparse_v2.py:196-202, transformer_predictor_v2.py:263-274) ----------------------
- * dense is [B, C, X, Y, Z] float32; cell = (coord - min) / stride                              */
+ * dense is [B, C, X, Y, Z] float32; cell = (coord - min) / stride.  A row whose cell lies outside the volume is
+ * skipped (to_dense) / reads as zero (from_dense) and sets *err_flag = 1 on the device (err_flag may be NULL); the
+ * host wrapper raises at its next synchronisation point, where MinkowskiEngine raises immediately.              */
 int pasco_to_dense(const float* feats, const int32_t* coords, int64_t n, int32_t C, const int32_t min_c[3],
                    const int32_t stride[3], float* dense, int32_t B, int32_t X, int32_t Y, int32_t Z,
-                   pasco_stream_t s);
+                   int32_t* err_flag, pasco_stream_t s);
 int pasco_from_dense(const float* dense, const int32_t* coords, int64_t n, int32_t C, const int32_t min_c[3],
                      const int32_t stride[3], float* feats, int32_t B, int32_t X, int32_t Y, int32_t Z,
-                     pasco_stream_t s);
+                     int32_t* err_flag, pasco_stream_t s);
 /* occupancy[b,x,y,z] = (sum_c |dense[b,c,x,y,z]|) != 0  → uint8 mask in (b,x,y,z) order */
 int pasco_dense_occupancy(const float* dense, int32_t B, int32_t C, int64_t cells, uint8_t* mask,
                           pasco_stream_t s);

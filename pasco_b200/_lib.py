@@ -35,8 +35,8 @@ PROTOTYPES = {
     "pasco_gather_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
     "pasco_scatter_rows": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p]),
     "pasco_gather_coords": (C.c_int, [_p, _p, _i64, _p, _p]),
-    "pasco_to_dense": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
-    "pasco_from_dense": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "pasco_to_dense": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "pasco_from_dense": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "pasco_dense_occupancy": (C.c_int, [_p, _i32, _i32, _i64, _p, _p]),
     "pasco_conv_packed_bytes": (_i64, [_i32, _i32, _i32]),
     "pasco_conv_pack_weights": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),

@@ -410,6 +410,7 @@ __global__ void k_dense_xfer(float* __restrict__ feats, const int4* __restrict__
         z = floor_div(q.w - g.min_c[2], g.stride[2]);
     if (q.x < 0 || q.x >= g.B || x < 0 || x >= g.X || y < 0 || y >= g.Y || z < 0 || z >= g.Z) {
       if (err) *err = 1;
+      if (!TO_DENSE) feats[t] = 0.f;      // a row outside the volume reads as zero (never uninitialised memory)
       continue;
     }
     int64_t d = ((int64_t)q.x * C + c) * cells + ((int64_t)x * g.Y + y) * g.Z + z;
@@ -432,22 +433,22 @@ static DenseGeom make_geom(const int32_t min_c[3], const int32_t stride[3], int 
 
 extern "C" int pasco_to_dense(const float* feats, const int32_t* coords, int64_t n, int32_t C, const int32_t min_c[3],
                               const int32_t stride[3], float* dense, int32_t B, int32_t X, int32_t Y, int32_t Z,
-                              pasco_stream_t s) {
+                              int32_t* err_flag, pasco_stream_t s) {
   PASCO_CHECK_ARG(stride[0] > 0 && stride[1] > 0 && stride[2] > 0, "pasco_to_dense: bad stride");
   if (n == 0 || C == 0) return 0;
   k_dense_xfer<true><<<grid_for(n * C, 256), 256, 0, (cudaStream_t)s>>>(
-      const_cast<float*>(feats), (const int4*)coords, n, C, make_geom(min_c, stride, B, X, Y, Z), dense, nullptr);
+      const_cast<float*>(feats), (const int4*)coords, n, C, make_geom(min_c, stride, B, X, Y, Z), dense, err_flag);
   PASCO_CHECK_LAUNCH("pasco_to_dense");
   return 0;
 }
 
 extern "C" int pasco_from_dense(const float* dense, const int32_t* coords, int64_t n, int32_t C,
                                 const int32_t min_c[3], const int32_t stride[3], float* feats, int32_t B, int32_t X,
-                                int32_t Y, int32_t Z, pasco_stream_t s) {
+                                int32_t Y, int32_t Z, int32_t* err_flag, pasco_stream_t s) {
   PASCO_CHECK_ARG(stride[0] > 0 && stride[1] > 0 && stride[2] > 0, "pasco_from_dense: bad stride");
   if (n == 0 || C == 0) return 0;
   k_dense_xfer<false><<<grid_for(n * C, 256), 256, 0, (cudaStream_t)s>>>(
-      feats, (const int4*)coords, n, C, make_geom(min_c, stride, B, X, Y, Z), const_cast<float*>(dense), nullptr);
+      feats, (const int4*)coords, n, C, make_geom(min_c, stride, B, X, Y, Z), const_cast<float*>(dense), err_flag);
   PASCO_CHECK_LAUNCH("pasco_from_dense");
   return 0;
 }

@@ -418,9 +418,9 @@ class _Convolution(MinkowskiModuleBase):
             raise RuntimeError(f"Channel size mismatch {x.F.shape[1]} != {self.in_channels}")
         cm, in_key = x.coordinate_manager, x.coordinate_map_key
         if self.use_mm:
-            out = x.F @ self.kernel                     # plain library GEMM, exactly as ME does for 1x1
-            if self.bias is not None:
-                out = out + self.bias
+            # ME does F.mm here; tall inputs with 64-multiple channels take the tcgen05 GEMM (ops.LinearTC), the rest
+            # stays the fp32 library GEMM
+            out = ops.linear(x.F, self.kernel.t(), self.bias.view(-1) if self.bias is not None else None)
             return SparseTensor(out, coordinate_map_key=in_key, coordinate_manager=cm)
         if self.is_transpose:
             if not self.expand_coordinates:
@@ -465,8 +465,13 @@ class MinkowskiBatchNorm(MinkowskiModuleBase):
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
                                  track_running_stats=track_running_stats)
 
+    def _group(self):
+        return None
+
     def forward(self, x):
-        return _like(x, self.bn(x.F))
+        # training-mode statistics + apply run in the fused row kernels (ops.BatchNormAct; the convolution that produced
+        # x already left its column sums); same parameters, buffers and running-statistics update as nn.BatchNorm1d
+        return _like(x, ops.batchnorm_rows(self.bn, x.F, ops.ACT_NONE, self._group()))
 
 
 class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
@@ -475,6 +480,13 @@ class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
         MinkowskiModuleBase.__init__(self)
         self.bn = nn.SyncBatchNorm(num_features, eps=eps, momentum=momentum, affine=affine,
                                    track_running_stats=track_running_stats, process_group=process_group)
+
+    def _group(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or not self.bn.training:
+            return None
+        g = self.bn.process_group if self.bn.process_group is not None else dist.group.WORLD
+        return g if dist.get_world_size(g) > 1 else None
 
     @classmethod
     def convert_sync_batchnorm(cls, module, process_group=None):

@@ -6,6 +6,7 @@ current stream and the autograd graph.  Row indices are int32, −1 = no row.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -50,6 +51,28 @@ def force_simt(flag: bool, kinds=None) -> None:
     global _FORCE_SIMT, _SIMT_KINDS
     _FORCE_SIMT = bool(flag) and kinds is None
     _SIMT_KINDS = set(kinds) if (flag and kinds is not None) else None
+
+
+_ERR = {}               # device → int32[1] error flag set by kernels (rows outside a dense volume); read at sync points
+
+
+def _err_flag(dev) -> torch.Tensor:
+    f = _ERR.get(dev)
+    if f is None:
+        f = _ERR[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return f
+
+
+def raise_pending_errors(dev=None) -> None:
+    """Raise what MinkowskiEngine raises immediately (a coordinate outside the dense volume) — called where the host
+    already synchronises (compact), and by tests."""
+    for d, f in list(_ERR.items()):
+        if dev is not None and d != dev:
+            continue
+        if int(f.item()) != 0:
+            f.zero_()
+            raise RuntimeError("pasco_b200: a coordinate lies outside the requested dense volume "
+                               "(SparseTensor.dense / to_sparse: check min_coordinate and shape)")
 
 
 def _i32(t: torch.Tensor) -> torch.Tensor:
@@ -159,6 +182,8 @@ def compact(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
     incl = torch.cumsum(counts, 0, dtype=torch.int32)       # ≤ ~1k elements: plumbing
     offsets = (incl - counts).contiguous()
     total = int(incl[-1].item())
+    if _ERR:
+        raise_pending_errors(dev)
     new_row = torch.empty(n, dtype=torch.int32, device=dev)
     kept = torch.empty(total, dtype=torch.int32, device=dev)
     call("pasco_mask_compact", ptr(m8), n, ptr(offsets), ptr(new_row), ptr(kept))
@@ -230,7 +255,8 @@ class ToDense(torch.autograd.Function):
         B, Cc, X, Y, Z = shape
         dense = torch.zeros(shape, dtype=torch.float32, device=feats.device)
         mc, st = _geom(min_c, stride)
-        call("pasco_to_dense", ptr(feats.contiguous()), ptr(coords), feats.shape[0], Cc, mc, st, ptr(dense), B, X, Y, Z)
+        call("pasco_to_dense", ptr(feats.contiguous()), ptr(coords), feats.shape[0], Cc, mc, st, ptr(dense), B, X, Y, Z,
+             ptr(_err_flag(feats.device)))
         ctx.save_for_backward(coords)
         ctx.meta = (tuple(min_c), tuple(stride), tuple(shape))
         return dense
@@ -244,9 +270,10 @@ class ToDense(torch.autograd.Function):
 
 def from_dense_raw(dense: torch.Tensor, coords: torch.Tensor, min_c, stride) -> torch.Tensor:
     B, Cc, X, Y, Z = dense.shape
-    feats = torch.empty(coords.shape[0], Cc, dtype=torch.float32, device=dense.device)
+    feats = torch.empty(coords.shape[0], Cc, dtype=torch.float32, device=dense.device)   # out-of-volume rows read as 0
     mc, st = _geom(min_c, stride)
-    call("pasco_from_dense", ptr(dense), ptr(coords), coords.shape[0], Cc, mc, st, ptr(feats), B, X, Y, Z)
+    call("pasco_from_dense", ptr(dense), ptr(coords), coords.shape[0], Cc, mc, st, ptr(feats), B, X, Y, Z,
+         ptr(_err_flag(dense.device)))
     return feats
 
 
@@ -264,7 +291,7 @@ class FromDense(torch.autograd.Function):
         B, Cc, X, Y, Z = shape
         dense = torch.zeros(shape, dtype=torch.float32, device=g.device)
         mc, st = _geom(min_c, stride)
-        call("pasco_to_dense", ptr(g.contiguous()), ptr(coords), g.shape[0], Cc, mc, st, ptr(dense), B, X, Y, Z)
+        call("pasco_to_dense", ptr(g.contiguous()), ptr(coords), g.shape[0], Cc, mc, st, ptr(dense), B, X, Y, Z, None)
         return dense, None, None, None
 
 
@@ -368,6 +395,8 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
+    global _PENDING_STATS
+    _PENDING_STATS = None            # statistics of an earlier launch never survive another convolution
     use_tc = _tc_ok(c_contract, c_out, kk, "dgrad" if transpose_w else "fwd")
     if use_tc and _USE_PLANES:
         hi, lo = split_planes(feats, in_scale, in_shift, in_act)
@@ -385,8 +414,8 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         call("pasco_conv_forward_tc", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act,
              ptr(stats), ptr(out), _PRECISION, 0, 0)
-        global _PENDING_STATS
-        _PENDING_STATS = (out.data_ptr(), out._version, tuple(out.shape), stats) if stats is not None else None
+        if stats is not None:
+            _PENDING_STATS = (weakref.ref(out), out.data_ptr(), out._version, tuple(out.shape), stats)
     else:
         assert in_scale is None and in_act == 0, "fused prologue needs the tensor-core path"
         if nbr is None:
@@ -408,8 +437,13 @@ def take_pending_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
     any in-place change since bumps the version), or None.  Consumed once."""
     global _PENDING_STATS
     pend, _PENDING_STATS = _PENDING_STATS, None
-    if pend is not None and pend[0] == x.data_ptr() and pend[1] == x._version and pend[2] == tuple(x.shape):
-        return pend[3]
+    if pend is None:
+        return None
+    ref, dptr, ver, shape, stats = pend
+    # the producing tensor must still be alive (a freed block re-used at the same address is another tensor) and x must
+    # be that storage, unmodified
+    if ref() is not None and dptr == x.data_ptr() and ver == x._version and shape == tuple(x.shape):
+        return stats
     return None
 
 
@@ -594,6 +628,42 @@ class BatchNormAct(torch.autograd.Function):
         return gx, gg, gb, None, None, None, None, None, None
 
 
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def _act_torch(z: torch.Tensor, act: int) -> torch.Tensor:
+    if act == ACT_RELU:
+        return torch.relu(z)
+    if act == ACT_LEAKY:
+        return torch.nn.functional.leaky_relu(z, 0.01)
+    return z
+
+
+def batchnorm_rows(bn, x: torch.Tensor, act: int = ACT_NONE, group=None) -> torch.Tensor:
+    """act(BatchNorm(x)) over the rows of x [N, C] with the parameters / running statistics of a torch
+    BatchNorm1d/3d/SyncBatchNorm module `bn`.  Training (or no running statistics): batch statistics through the fused
+    kernels (ops.BatchNormAct).  Eval: a per-channel affine — through one fused kernel when no gradient is needed, through
+    differentiable torch ops otherwise (frozen-BN fine-tuning keeps its graph)."""
+    use_batch_stats = bn.training or bn.running_mean is None
+    if use_batch_stats:
+        if bn.training and bn.num_batches_tracked is not None:
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+        gamma = bn.weight if bn.weight is not None else torch.ones(x.shape[1], device=x.device)
+        beta = bn.bias if bn.bias is not None else torch.zeros(x.shape[1], device=x.device)
+        mom = bn.momentum
+        if mom is None and bn.num_batches_tracked is not None:          # cumulative moving average
+            mom = 1.0 / float(bn.num_batches_tracked)
+        rm, rv = (bn.running_mean, bn.running_var) if bn.training else (None, None)
+        return BatchNormAct.apply(x, gamma, beta, bn.eps, act, group, rm, rv, mom)
+    w = bn.weight if bn.weight is not None else 1.0
+    scale = w * torch.rsqrt(bn.running_var + bn.eps)
+    shift = (bn.bias if bn.bias is not None else 0.0) - bn.running_mean * scale
+    if torch.is_grad_enabled() and (x.requires_grad or scale.requires_grad or shift.requires_grad):
+        return _act_torch(x * scale + shift, act)
+    return affine_act(x.contiguous(), scale.contiguous(), shift.contiguous(), act)
+
+
 # ----------------------------------------------------------------------------------------------
 # masked cross-attention of a few queries over all voxels (MaskPLS decoder)
 # ----------------------------------------------------------------------------------------------
@@ -658,6 +728,8 @@ def _linear_tc_ok(n_rows: int, cin: int, cout: int) -> bool:
 
 def _gemm_rows(x: torch.Tensor, w_nk: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> None:
     """out[:, :] = x @ w_nkᵀ (+ bias) with w_nk [N, K] row-major (torch Linear layout), N in chunks of <= 256 columns."""
+    global _PENDING_STATS
+    _PENDING_STATS = None
     n_rows, kdim = x.shape
     N = w_nk.shape[0]
     assert x.is_contiguous() and out.is_contiguous() and kdim % 64 == 0 and N % 16 == 0
