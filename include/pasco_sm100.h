@@ -160,17 +160,23 @@ int pasco_conv_forward_splitk(const float* in, int64_t n_in, const int32_t* nbr,
  * split, same MMA order); measured speeds are in DESIGN.md section 3.4.                                             */
 int pasco_conv_set_variant(int32_t variant);
 
-/* Pre-split input path: x = hi + lo (bf16 planes, lo = NULL for precision 1), produced once per tensor — optionally
- * fused with y = act(x*scale + shift) (BatchNorm + ReLU of the producing layer) — so that the gather of the convolution
- * is done by the TMA engine (cp.async.bulk.tensor tile::gather4: 4 arbitrary rows per instruction, written straight
- * into the swizzled UMMA tiles).  A plane holds N + PASCO_PLANE_PAD_ROWS rows of C bf16: pasco_split_planes zero-fills
- * the pad, and the convolution redirects missing neighbours (-1) into it.                                           */
-#define PASCO_PLANE_PAD_ROWS 1024
+/* Plane-gather path (the default for every gathered convolution): the activations are split ONCE per tensor into bf16
+ * planes x = hi + lo (lo = NULL for precision 1) by pasco_split_planes — optionally fused with y = act(x*scale + shift),
+ * the BatchNorm + activation of the producing layer — and the convolution / weight-gradient producers move plane rows
+ * with 16-byte cp.async copies straight into the swizzled UMMA tiles (missing neighbours are zero-fill copies that touch
+ * no memory).  Planes are bf16 [N, C] with a row pitch in ELEMENTS (0 = C); C % 8 == 0.
+ * pasco_conv_forward_planes: forward and input gradient (same contract as pasco_conv_forward_tc: koff_map, bias, fused
+ * BatchNorm statistics of `out` in `stats`);  pasco_conv_wgrad_planes: dW (zeroed by the caller) from the planes of the
+ * layer input and of the output gradient.                                                                          */
 int pasco_split_planes(const float* x, int64_t n, int32_t C, int64_t pitch, const float* scale, const float* shift,
                        int32_t act, void* hi, void* lo, pasco_stream_t s);
 int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out,
                               int32_t Cin, int32_t Cout, const void* packed_w, const int32_t* koff_map, const float* bias,
-                              float* out, int32_t precision, int64_t out_pitch, pasco_stream_t s);
+                              double* stats, float* out, int32_t precision, int64_t plane_pitch, int64_t out_pitch,
+                              pasco_stream_t s);
+int pasco_conv_wgrad_planes(const void* in_hi, const void* in_lo, int64_t n_in, const int32_t* nbr, int32_t K,
+                            int64_t n_out, int32_t Cin, int32_t Cout, const void* g_hi, const void* g_lo, float* dW,
+                            int32_t precision, int64_t in_pitch, int64_t gout_pitch, pasco_stream_t s);
 
 /* dW[k] = sum_o in[nbr[k,o],:]^T @ gout[o,:]   (tcgen05, MN-major operands); dW float32 [K,Cin,Cout] zeroed by caller */
 int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t* nbr, int32_t K, int64_t n_out, int32_t Cin,

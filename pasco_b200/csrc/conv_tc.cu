@@ -63,6 +63,11 @@ struct ConvParams {
   int koff_base, koff_step;   // weight slice of table row k = koff_base + koff_step * k
   int ksplit, kchunk;         // split-K: work item v = (tile group v / ksplit, offsets [ks*kchunk, (ks+1)*kchunk)), partial
                               // results go to out + ks * n_out * out_pitch (summed by k_splitk_reduce)
+  // k_conv_pl only: the input as pre-split bf16 planes x = hi + lo, [n_in, Cin] each with row pitch pl_pitch (elements)
+  const uint16_t* pl_hi;
+  const uint16_t* pl_lo;
+  int64_t pl_pitch;
+  int pl_depth;               // slots whose copies are in flight per producer thread before the oldest is published
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -826,6 +831,200 @@ __global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Plane-gather variant: the input arrives PRE-SPLIT as bf16 planes (hi [+ lo]) and the producers only move bytes
+// ------------------------------------------------------------------------------------------------------------
+// ncu of k_conv_tc (round 1): 3.5 long-scoreboard stall cycles per issued instruction, L2 at 15 % — every gathered
+// fp32 value crosses the register file and is converted 27x (once per kernel offset).  Here the split x = hi + lo is
+// done ONCE per tensor by the producing pass (k_split_planes / the BatchNorm apply), and a gather warp issues
+// 16-byte cp.async (LDGSTS) copies straight from the plane rows into the 128-byte-swizzled UMMA tile:
+//   * no registers on the data path, so `pl_depth` whole A stages (32 KB each in fp32 mode) are in flight per SM;
+//   * a missing neighbour is a ZERO-FILL copy (src-size 0): no global or L2 traffic at all for the ~38 % of
+//     (row, offset) pairs that have no neighbour — the TMA gather4 variant of round 1 had to fetch a zero row for each;
+//   * 8 copies per lane per slot instead of ~600 gather/convert/store instructions.
+// Completion: one cp.async group per slot; a warp publishes slot n - pl_depth after cp.async.wait_group, a
+// generic→async proxy fence and one mbarrier arrive (same hand-off as the register kernel's st.shared path).
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups of this thread are pending
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int n_op = (NSPLIT == 3) ? 2 : 1;
+  const int b_tile = p.Cout * 128;
+  const int a_stage_bytes = n_op * A_TILE_BYTES;
+  const int b_stage_bytes = n_op * b_tile;
+  const int T = p.tiles_per_group;
+  uint8_t* a_smem = smem;                                           // [sa][A_hi | A_lo]
+  uint8_t* b_smem = smem + (size_t)p.sa * a_stage_bytes;            // [sb][B_hi | B_lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)p.sb * b_stage_bytes);
+  uint64_t* afull = bars;                         // [MAX_STAGES]
+  uint64_t* aempty = bars + MAX_STAGES;           // [MAX_STAGES]
+  uint64_t* bfull = bars + 2 * MAX_STAGES;        // [MAX_STAGES]
+  uint64_t* bempty = bars + 3 * MAX_STAGES;       // [MAX_STAGES]
+  uint64_t* tfull = bars + 4 * MAX_STAGES;        // [2]
+  uint64_t* tempty = bars + 4 * MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
+  double* stat_acc = p.stats ? reinterpret_cast<double*>(tmem_slot + 4) : nullptr;   // [2*Cout]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.Cin / KBLK;
+  const int64_t num_tiles = (p.n_out + BLOCK_M - 1) / BLOCK_M;
+  const int64_t num_groups = (num_tiles + T - 1) / T;
+  const int acc_cols = T * p.Cout;
+
+  if (stat_acc)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += NUM_THREADS) stat_acc[i] = 0.0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(smem_u32(afull + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(aempty + s), 1);
+      mbar_init(smem_u32(bfull + s), 1);
+      mbar_init(smem_u32(bempty + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(tfull + b), 1);
+      mbar_init(smem_u32(tempty + b), NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  Pipe pl;
+  pl.a_smem = a_smem; pl.b_smem = b_smem;
+  pl.afull = afull; pl.aempty = aempty; pl.bfull = bfull; pl.bempty = bempty; pl.tfull = tfull; pl.tempty = tempty;
+  pl.tmem_base = tmem_base;
+  pl.stat_acc = stat_acc;
+  pl.a_stage_bytes = a_stage_bytes; pl.b_stage_bytes = b_stage_bytes; pl.b_tile = b_tile;
+  pl.KB = KB; pl.T = T; pl.acc_cols = acc_cols; pl.num_tiles = num_tiles; pl.num_groups = num_groups;
+
+  if (warp < NUM_GATHER_WARPS) {
+    // ===================================== plane-gather producers =====================================
+    // Warp w owns tile rows 16w .. 16w+15.  One copy instruction moves 4 rows: lane = (row sub-index 0..3, 16-byte
+    // chunk 0..7 of the 128-byte row); 4 instructions per plane per slot.  Lane j < 16 holds the neighbour index of
+    // row 16w + j (one coalesced 64-byte load per slot, fetched PF slots ahead), distributed by shuffles.
+    const int ch = lane & 7, sub = lane >> 3;
+    const int64_t num_items = num_groups * p.ksplit;
+    struct It {
+      int64_t v, group;
+      int k, k1, kb, t, t_eff;
+      bool valid;
+    };
+    auto enter = [&](It& it, int64_t v) {
+      it.v = v;
+      it.valid = v < num_items;
+      it.kb = 0; it.t = 0;
+      if (it.valid) {
+        it.group = v / p.ksplit;
+        it.k = (int)(v % p.ksplit) * p.kchunk;
+        it.k1 = it.k + p.kchunk < p.K ? it.k + p.kchunk : p.K;
+        const int64_t rem = num_tiles - it.group * T;
+        it.t_eff = rem < T ? (int)rem : T;
+      }
+    };
+    auto advance = [&](It& it) {
+      if (++it.t < it.t_eff) return;
+      it.t = 0;
+      if (++it.kb < KB) return;
+      it.kb = 0;
+      if (++it.k < it.k1) return;
+      enter(it, it.v + gridDim.x);
+    };
+    auto load_idx = [&](const It& it) -> int {
+      int idx = -1;
+      if (it.valid && lane < ROWS_PER_WARP) {
+        const int64_t row = (it.group * T + it.t) * BLOCK_M + warp * ROWS_PER_WARP + lane;
+        if (row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)it.k * p.n_out + row) : (int)row;
+      }
+      return idx;
+    };
+    constexpr int PF = 4;
+    It cur, pf;
+    enter(cur, blockIdx.x);
+    pf = cur;
+    int q[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      q[i] = load_idx(pf);
+      if (pf.valid) advance(pf);
+    }
+    const int D = p.pl_depth;
+    int stage = 0, astage = 0;        // next stage to fill / next stage to publish
+    uint32_t phase = 0;
+    int pending = 0;
+    auto publish_oldest = [&]() {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(afull + astage));
+      if (++astage == p.sa) astage = 0;
+      --pending;
+    };
+    while (cur.valid) {
+      const int myidx = q[0];
+#pragma unroll
+      for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
+      q[PF - 1] = load_idx(pf);
+      if (pf.valid) advance(pf);
+
+      mbar_wait(smem_u32(aempty + stage), phase ^ 1);
+      const uint32_t dst0 = smem_u32(a_smem + (size_t)stage * a_stage_bytes);
+      const int64_t coff = (int64_t)cur.kb * KBLK + ch * 8;
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_WARP / 4; ++i) {
+        const int r = warp * ROWS_PER_WARP + i * 4 + sub;
+        const int idx = __shfl_sync(0xffffffffu, myidx, i * 4 + sub);
+        const uint32_t nbytes = idx >= 0 ? 16u : 0u;
+        const int64_t eoff = (int64_t)(idx >= 0 ? idx : 0) * p.pl_pitch + coff;
+        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
+        cp_async16_zfill(dst0 + off, p.pl_hi + eoff, nbytes);
+        if (NSPLIT == 3) cp_async16_zfill(dst0 + A_TILE_BYTES + off, p.pl_lo + eoff, nbytes);
+      }
+      cp_async_commit();
+      ++pending;
+      if (++stage == p.sa) {
+        stage = 0;
+        phase ^= 1;
+      }
+      advance(cur);
+      if (pending > D) {
+        cp_async_wait_dyn(D);
+        publish_oldest();
+      }
+    }
+    cp_async_wait<0>();
+    while (pending > 0) publish_oldest();
+  } else if (warp == LOAD_WARP) {
+    if (lane == 0) role_weight_loader(p, pl);
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) role_mma<NSPLIT>(p, pl);
+  } else {
+    role_epilogue(p, pl, warp - NUM_GATHER_WARPS, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 // 0 = register-gather kernel everywhere (default: it is the faster one in fp32 mode),
 // 1 = TMA-gather kernel where eligible; PASCO_CONV_TMA overrides at load
 int& conv_variant() {
@@ -937,6 +1136,7 @@ int conv_forward_impl(const float* in, int64_t n_in, const int32_t* nbr, int32_t
   p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
   PASCO_CHECK_ARG(p.out_pitch % 4 == 0 && p.in_pitch % 4 == 0, "pasco_conv_forward_tc: pitches must be multiples of 4 floats");
   p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = in_act;
+  p.pl_hi = nullptr; p.pl_lo = nullptr; p.pl_pitch = 0; p.pl_depth = 0;
   p.sa = sa; p.sb = sb; p.tiles_per_group = T; p.tmem_cols = pow2_cols(2 * T * Cout);
   p.koff_base = 0; p.koff_step = 1;
   if (koff_map) {
@@ -1015,6 +1215,77 @@ extern "C" int pasco_conv_forward_tc(const float* in, int64_t n_in, const int32_
                                      pasco_stream_t s) {
   return conv_forward_impl(in, n_in, nbr, K, n_out, Cin, Cout, packed_w, koff_map, bias, in_scale, in_shift, in_act, stats, out,
                            precision, in_pitch, out_pitch, 1, nullptr, s);
+}
+
+extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t n_in, const int32_t* nbr, int32_t K,
+                                         int64_t n_out, int32_t Cin, int32_t Cout, const void* packed_w,
+                                         const int32_t* koff_map, const float* bias, double* stats, float* out,
+                                         int32_t precision, int64_t plane_pitch, int64_t out_pitch, pasco_stream_t s) {
+  PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_forward_planes: precision must be 1 or 3");
+  PASCO_CHECK_ARG(hi != nullptr && (precision == 1 || lo != nullptr), "pasco_conv_forward_planes: missing plane (precision 3 needs hi and lo)");
+  PASCO_CHECK_ARG(Cin % KBLK == 0, "pasco_conv_forward_planes: Cin (%d) must be a multiple of 64", Cin);
+  PASCO_CHECK_ARG(Cout % 16 == 0 && Cout >= 16 && Cout <= 256, "pasco_conv_forward_planes: Cout (%d) must be a multiple of 16 in [16,256]", Cout);
+  PASCO_CHECK_ARG(K >= 1 && K <= 1024, "pasco_conv_forward_planes: K (%d) out of range", K);
+  const int64_t pitch = plane_pitch > 0 ? plane_pitch : Cin;
+  PASCO_CHECK_ARG(pitch % 8 == 0 && (((uintptr_t)hi | (uintptr_t)lo | (uintptr_t)out | (uintptr_t)packed_w) & 15) == 0,
+                  "pasco_conv_forward_planes: planes must be 16-byte aligned with a pitch multiple of 8 elements");
+  (void)n_in;
+  if (n_out == 0) return 0;
+  int dev = 0, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int n_op = precision == 3 ? 2 : 1;
+  const int a_stage = n_op * A_TILE_BYTES, b_stage = n_op * Cout * 128;
+  const int64_t tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
+  int T = 256 / Cout;
+  if (T < 1) T = 1;
+  if (T > 4) T = 4;
+  while (T > 1 && tiles < (int64_t)T * num_sms()) T >>= 1;
+  const int fixed = 1024 + (4 * MAX_STAGES + 4) * 8 + 16 + (stats ? 2 * Cout * 8 : 0);
+  int sb = 2;
+  int sa = (smem_optin - fixed - sb * b_stage) / a_stage;
+  if (sa > MAX_STAGES) sa = MAX_STAGES;
+  PASCO_CHECK_ARG(sa >= 2, "pasco_conv_forward_planes: not enough shared memory (Cout=%d)", Cout);
+  ConvParams p;
+  p.in = nullptr; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w; p.bias = bias;
+  p.in_scale = nullptr; p.in_shift = nullptr; p.out = out; p.stats = stats;
+  p.n_out = n_out;
+  p.out_pitch = out_pitch > 0 ? out_pitch : Cout;
+  p.in_pitch = Cin;
+  PASCO_CHECK_ARG(p.out_pitch % 4 == 0, "pasco_conv_forward_planes: out_pitch must be a multiple of 4 floats");
+  p.K = K; p.Cin = Cin; p.Cout = Cout; p.in_act = 0;
+  p.sa = sa; p.sb = sb; p.tiles_per_group = T; p.tmem_cols = pow2_cols(2 * T * Cout);
+  p.ksplit = 1; p.kchunk = K;
+  p.koff_base = 0; p.koff_step = 1;
+  if (koff_map) {
+    bool ident = true, rev = true;
+    for (int k = 0; k < K; ++k) {
+      ident = ident && koff_map[k] == k;
+      rev = rev && koff_map[k] == K - 1 - k;
+    }
+    PASCO_CHECK_ARG(ident || rev, "pasco_conv_forward_planes: koff_map must be the identity or the reversal");
+    if (!ident) { p.koff_base = K - 1; p.koff_step = -1; }
+  }
+  p.pl_hi = (const uint16_t*)hi; p.pl_lo = (const uint16_t*)lo; p.pl_pitch = pitch;
+  static const int depth_env = [] { const char* e = getenv("PASCO_PL_DEPTH"); return e ? atoi(e) : 0; }();
+  p.pl_depth = sa - 1;                       // all but one stage in flight; the MMA works on the remaining one
+  if (depth_env > 0 && depth_env < p.pl_depth) p.pl_depth = depth_env;
+  if (p.pl_depth > 7) p.pl_depth = 7;
+  const size_t smem = (size_t)sa * a_stage + (size_t)sb * b_stage + fixed;
+  const int64_t groups = (tiles + T - 1) / T;
+  const int grid = (int)(groups < num_sms() ? groups : num_sms());
+  auto launch = [&](auto kern) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) kern<<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+    return err;
+  };
+  const cudaError_t e = precision == 3 ? launch(k_conv_pl<3>) : launch(k_conv_pl<1>);
+  if (e != cudaSuccess) {
+    set_error("pasco_conv_forward_planes: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
+    return -1;
+  }
+  PASCO_CHECK_LAUNCH("pasco_conv_forward_planes");
+  return 0;
 }
 
 extern "C" int64_t pasco_conv_splitk_workspace_bytes(int32_t K, int64_t n_out, int32_t Cout) {

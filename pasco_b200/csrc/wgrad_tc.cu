@@ -365,6 +365,265 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Plane-gather variant of the weight gradient: both operands arrive as pre-split bf16 planes
+// ------------------------------------------------------------------------------------------------------------
+// Same UMMA view, TMEM residency, passes and epilogue as k_wgrad_tc; the producers only move bytes: 16-byte cp.async
+// copies from the `in` planes (gathered rows; a missing neighbour is a zero-fill copy that touches no memory) and from
+// the `gout` planes (contiguous rows) straight into the 128-byte-swizzled tiles.  One cp.async group per slot
+// (slot 0 of a row tile = the whole gout tile, slots 1.. = one unit of two gathered sub-tiles each); a warp publishes
+// slot n - depth after cp.async.wait_group + a generic→async proxy fence.  Round-1 k_wgrad_tc spent ~600 gather /
+// convert / store instructions per sub-tile and ran at 15 % tensor-pipe utilisation, 2.4x slower than the forward.
+struct WgradPlParams {
+  const uint16_t* in_hi;
+  const uint16_t* in_lo;
+  const uint16_t* g_hi;
+  const uint16_t* g_lo;
+  const int32_t* nbr;
+  float* dW;
+  int64_t n_out;
+  int64_t in_pitch, gout_pitch;   // row strides (bf16 elements)
+  int K, Cin, Cout;
+  int stages, tmem_cols, depth;
+  int units_per_pass, num_units, num_subs, passes, ctas_per_pass;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_constant__ WgradPlParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int n_op = (NSPLIT == 3) ? 2 : 1;
+  const int NB = p.Cout / 64;                    // 64-column blocks of gout
+  const int g_bytes = n_op * NB * WG_SUB_BYTES;  // one gout tile (hi blocks [+ lo blocks])
+  const int a_bytes = n_op * 2 * WG_SUB_BYTES;   // one stage: two sub-tiles (hi, hi [, lo, lo])
+  uint8_t* g_smem = smem;                        // [2][g_bytes]
+  uint8_t* a_smem = smem + 2 * (size_t)g_bytes;  // [stages][a_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)p.stages * a_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* gfull_bar = bars + 2 * MAX_STAGES;       // [2]
+  uint64_t* gempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
+  uint64_t* done_bar = bars + 2 * MAX_STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int CB = p.Cin / 64;
+  const int pass = blockIdx.x % p.passes;
+  const int cta_in_pass = blockIdx.x / p.passes;
+  const int unit0 = pass * p.units_per_pass;
+  const int nunits = min(p.units_per_pass, p.num_units - unit0);
+  const int64_t num_rt = (p.n_out + WG_R - 1) / WG_R;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(full_bar + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(gfull_bar + b), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(gempty_bar + b), 1);
+    }
+    mbar_init(smem_u32(done_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int spr = 1 + nunits;                // slots per row tile: the gout tile, then one per unit
+
+  if (warp < NUM_GATHER_WARPS) {
+    // lane = (row sub-index 0..3, 16-byte chunk 0..7): one copy instruction moves 4 of the warp's 8 tile rows
+    const int ch = lane & 7, sub = lane >> 3;
+    const int64_t stride_rt = p.ctas_per_pass;
+    // neighbour indices of a unit slot: lanes 0-7 = rows of sub-tile 0, lanes 8-15 = rows of sub-tile 1
+    auto load_idx = [&](int64_t rt, int j) -> int {
+      int idx = -1;
+      if (j > 0 && rt < num_rt && lane < 16) {
+        const int sb = (unit0 + (j - 1)) * 2 + (lane >> 3);
+        const int64_t row = rt * WG_R + warp * WROWS + (lane & 7);
+        if (sb < p.num_subs && row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)(sb / CB) * p.n_out + row) : (int)row;
+      }
+      return idx;
+    };
+    constexpr int PF = 4;
+    int64_t c_rt = cta_in_pass, f_rt = cta_in_pass, a_rt = cta_in_pass;     // issue / index-prefetch / publish cursors
+    int c_j = 0, f_j = 0, a_j = 0;
+    int q[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      q[i] = load_idx(f_rt, f_j);
+      if (++f_j == spr) { f_j = 0; f_rt += stride_rt; }
+    }
+    const int D = p.depth;
+    int stage = 0, astage = 0, git = 0, agit = 0, pending = 0;
+    uint32_t phase = 0;
+    auto publish_oldest = [&]() {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (a_j == 0) {
+        if (lane == 0) mbar_arrive(smem_u32(gfull_bar + (agit & 1)));
+        ++agit;
+      } else {
+        if (lane == 0) mbar_arrive(smem_u32(full_bar + astage));
+        if (++astage == p.stages) astage = 0;
+      }
+      if (++a_j == spr) { a_j = 0; a_rt += stride_rt; }
+      --pending;
+    };
+    while (c_rt < num_rt) {
+      const int myidx = q[0];
+#pragma unroll
+      for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
+      q[PF - 1] = load_idx(f_rt, f_j);
+      if (++f_j == spr) { f_j = 0; f_rt += stride_rt; }
+
+      if (c_j == 0) {
+        // ---- the gout tile of this row tile: [64 rows][Cout] per plane, contiguous rows ----
+        const int gb = git & 1;
+        mbar_wait(smem_u32(gempty_bar + gb), ((git >> 1) & 1) ^ 1);
+        const uint32_t g0 = smem_u32(g_smem + (size_t)gb * g_bytes);
+#pragma unroll
+        for (int i = 0; i < WROWS / 4; ++i) {
+          const int r = warp * WROWS + i * 4 + sub;
+          const int64_t row = c_rt * WG_R + r;
+          const uint32_t nbytes = row < p.n_out ? 16u : 0u;
+          const int64_t eoff = (row < p.n_out ? row : 0) * p.gout_pitch + ch * 8;
+          const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
+          for (int nb = 0; nb < NB; ++nb) {
+            cp_async16_zfill(g0 + (uint32_t)nb * WG_SUB_BYTES + off, p.g_hi + eoff + nb * 64, nbytes);
+            if (NSPLIT == 3) cp_async16_zfill(g0 + (uint32_t)(NB + nb) * WG_SUB_BYTES + off, p.g_lo + eoff + nb * 64, nbytes);
+          }
+        }
+        ++git;
+      } else {
+        // ---- one unit: two gathered [64 rows][64 ch] sub-tiles ----
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+        const uint32_t a0 = smem_u32(a_smem + (size_t)stage * a_bytes);
+        const int sb0 = (unit0 + (c_j - 1)) * 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int sbi = sb0 + h;
+          const int cb = sbi < p.num_subs ? sbi % CB : 0;
+#pragma unroll
+          for (int i = 0; i < WROWS / 4; ++i) {
+            const int r = warp * WROWS + i * 4 + sub;
+            const int idx = __shfl_sync(0xffffffffu, myidx, h * 8 + i * 4 + sub);
+            const uint32_t nbytes = idx >= 0 ? 16u : 0u;
+            const int64_t eoff = (int64_t)(idx >= 0 ? idx : 0) * p.in_pitch + cb * 64 + ch * 8;
+            const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
+            cp_async16_zfill(a0 + (uint32_t)h * WG_SUB_BYTES + off, p.in_hi + eoff, nbytes);
+            if (NSPLIT == 3) cp_async16_zfill(a0 + (uint32_t)(2 + h) * WG_SUB_BYTES + off, p.in_lo + eoff, nbytes);
+          }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      cp_async_commit();
+      ++pending;
+      if (++c_j == spr) { c_j = 0; c_rt += stride_rt; }
+      if (pending > D) {
+        cp_async_wait_dyn(D);
+        publish_oldest();
+      }
+    }
+    cp_async_wait<0>();
+    while (pending > 0) publish_oldest();
+    // epilogue (gather warps 0-3): once the CTA's last MMA has retired, add the partial dW
+    if (warp < 4) {
+      const int qd = warp;
+      if (cta_in_pass < num_rt) {
+        mbar_wait(smem_u32(done_bar), 0);
+        tc_fence_after();
+        const int L = qd * 32 + lane;  // accumulator row = channel within the unit
+        for (int u = 0; u < nunits; ++u) {
+          const int sbi = (unit0 + u) * 2 + (L >> 6);
+          const bool ok = sbi < p.num_subs;
+          const int k = ok ? sbi / CB : 0;
+          const int cb = ok ? sbi - k * CB : 0;
+          float* drow = p.dW + ((int64_t)k * p.Cin + cb * 64 + (L & 63)) * p.Cout;
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(u * p.Cout);
+          for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int git = 0;
+      for (int64_t rt = cta_in_pass; rt < num_rt; rt += p.ctas_per_pass, ++git) {
+        const int gb = git & 1;
+        mbar_wait(smem_u32(gfull_bar + gb), (git >> 1) & 1);
+        tc_fence_after();
+        const uint32_t g_hi = smem_u32(g_smem + (size_t)gb * g_bytes);
+        const uint32_t g_lo = g_hi + NB * WG_SUB_BYTES;
+        for (int u = 0; u < nunits; ++u) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(a_smem + (size_t)stage * a_bytes);
+          const uint32_t a_lo = a_hi + 2 * WG_SUB_BYTES;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.Cout);
+#pragma unroll
+          for (int j = 0; j < WG_R / 16; ++j) {
+            const uint32_t acc = (git > 0 || j > 0) ? 1u : 0u;
+            const uint64_t da_hi = make_desc_sw128(a_hi + j * 2048, WG_SUB_BYTES, 1024);
+            const uint64_t db_hi = make_desc_sw128(g_hi + j * 2048, WG_SUB_BYTES, 1024);
+            mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
+            if (NSPLIT == 3) {
+              const uint64_t da_lo = make_desc_sw128(a_lo + j * 2048, WG_SUB_BYTES, 1024);
+              const uint64_t db_lo = make_desc_sw128(g_lo + j * 2048, WG_SUB_BYTES, 1024);
+              mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
+              mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+            }
+          }
+          mma_commit(smem_u32(empty_bar + stage));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(smem_u32(gempty_bar + gb));
+      }
+      mma_commit(smem_u32(done_bar));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 int pow2_cols(int c) {
   int v = 32;
   while (v < c) v <<= 1;
@@ -425,5 +684,67 @@ extern "C" int pasco_conv_wgrad_tc(const float* in, int64_t n_in, const int32_t*
     return -1;
   }
   PASCO_CHECK_LAUNCH("pasco_conv_wgrad_tc");
+  return 0;
+}
+
+extern "C" int pasco_conv_wgrad_planes(const void* in_hi, const void* in_lo, int64_t n_in, const int32_t* nbr, int32_t K,
+                                       int64_t n_out, int32_t Cin, int32_t Cout, const void* g_hi, const void* g_lo,
+                                       float* dW, int32_t precision, int64_t in_pitch, int64_t gout_pitch, pasco_stream_t s) {
+  PASCO_CHECK_ARG(precision == 1 || precision == 3, "pasco_conv_wgrad_planes: precision must be 1 or 3");
+  PASCO_CHECK_ARG(in_hi && g_hi && (precision == 1 || (in_lo && g_lo)), "pasco_conv_wgrad_planes: missing plane");
+  PASCO_CHECK_ARG(Cin % 64 == 0 && Cout % 64 == 0 && Cout <= 256,
+                  "pasco_conv_wgrad_planes: Cin (%d) and Cout (%d) must be multiples of 64, Cout <= 256", Cin, Cout);
+  (void)n_in;
+  if (n_out == 0) return 0;
+  int dev = 0, smem_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int n_op = precision == 3 ? 2 : 1;
+  const int g_bytes = n_op * (Cout / 64) * WG_SUB_BYTES;
+  const int a_bytes = n_op * 2 * WG_SUB_BYTES;
+  const int fixed = 1024 + (2 * MAX_STAGES + 6) * 8 + 32;
+  int stages = (smem_optin - fixed - 2 * g_bytes) / a_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  PASCO_CHECK_ARG(stages >= 2, "pasco_conv_wgrad_planes: not enough shared memory");
+  WgradPlParams p;
+  p.in_hi = (const uint16_t*)in_hi; p.in_lo = (const uint16_t*)in_lo; p.g_hi = (const uint16_t*)g_hi; p.g_lo = (const uint16_t*)g_lo;
+  p.nbr = nbr; p.dW = dW;
+  p.n_out = n_out; p.K = K; p.Cin = Cin; p.Cout = Cout;
+  p.in_pitch = in_pitch > 0 ? in_pitch : Cin;
+  p.gout_pitch = gout_pitch > 0 ? gout_pitch : Cout;
+  PASCO_CHECK_ARG(p.in_pitch % 8 == 0 && p.gout_pitch % 8 == 0 &&
+                  (((uintptr_t)in_hi | (uintptr_t)in_lo | (uintptr_t)g_hi | (uintptr_t)g_lo) & 15) == 0,
+                  "pasco_conv_wgrad_planes: planes must be 16-byte aligned with pitches multiple of 8 elements");
+  p.stages = stages;
+  p.depth = stages - 1 > 7 ? 7 : stages - 1;
+  static const int depth_env = [] { const char* e = getenv("PASCO_PL_DEPTH"); return e ? atoi(e) : 0; }();
+  if (depth_env > 0 && depth_env < p.depth) p.depth = depth_env;
+  p.num_subs = K * (Cin / 64);
+  p.num_units = (p.num_subs + 1) / 2;
+  p.units_per_pass = 512 / Cout;
+  if (p.units_per_pass > p.num_units) p.units_per_pass = p.num_units;
+  p.tmem_cols = pow2_cols(p.units_per_pass * Cout);
+  p.passes = (p.num_units + p.units_per_pass - 1) / p.units_per_pass;
+  p.units_per_pass = (p.num_units + p.passes - 1) / p.passes;   // balance the passes (8+6 → 7+7)
+  const int64_t num_rt = (n_out + WG_R - 1) / WG_R;
+  int cpp = num_sms() / p.passes;
+  if (cpp < 1) cpp = 1;
+  if (cpp > num_rt) cpp = (int)num_rt;
+  p.ctas_per_pass = cpp;
+  const size_t smem = (size_t)2 * g_bytes + (size_t)stages * a_bytes + fixed;
+  const int grid = p.passes * cpp;
+  cudaError_t e;
+  if (precision == 3) {
+    e = cudaFuncSetAttribute(k_wgrad_pl<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_wgrad_pl<3><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(k_wgrad_pl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_wgrad_pl<1><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+  }
+  if (e != cudaSuccess) {
+    set_error("pasco_conv_wgrad_planes: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
+    return -1;
+  }
+  PASCO_CHECK_LAUNCH("pasco_conv_wgrad_planes");
   return 0;
 }

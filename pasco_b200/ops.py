@@ -26,8 +26,8 @@ _SIMT_KINDS = None      # validation switch: subset of {'fwd','dgrad','wgrad'} f
 _SPLIT_K = True          # few-tile / many-offset convs (dense bottleneck) are split over the offsets
 _FUSE_BN_STATS = True    # forward convs leave their output's column statistics for the BatchNorm that follows
 _PENDING_STATS = None
-_USE_PLANES = False     # optional: forward / input-gradient convs gather pre-split bf16 planes with cp.async
-                        # (conv_planes.cu; measured 1.16 vs 1.38 ms at C=64 incl. the split pass, slower at C>=128)
+_USE_PLANES = True      # gathered convs (K > 1) read pre-split bf16 planes with zero-fill cp.async copies (k_conv_pl /
+                        # k_wgrad_pl); False = the round-1 register-gather kernels (kept for cross-checks)
 PROFILE = None          # bench.py sets this to a list: (kind, start_event, end_event, meta) per conv launch
 PAIR_COUNTS = {}        # nbr.data_ptr() → 0-dim device tensor with the number of valid pairs (profiling only)
 CALLS = 0               # number of C-ABI compute calls (each launches >= 1 kernel of ours)
@@ -358,17 +358,17 @@ def use_planes(flag: bool) -> None:
     _USE_PLANES = bool(flag)
 
 
-PLANE_PAD = 1024    # PASCO_PLANE_PAD_ROWS
-
-
 def split_planes(x: torch.Tensor, scale=None, shift=None, act: int = 0):
-    """x fp32 [N,C] → (hi, lo) bf16 planes of act(x*scale+shift), each N + PLANE_PAD rows (the pad is zero: missing
-    neighbours are gathered from it); lo is None in bf16 mode."""
+    """x fp32 [N,C] → (hi, lo) bf16 planes [N,C] of act(x*scale+shift) with x ≈ hi + lo; lo is None in bf16 mode."""
     n, c = x.shape
-    hi = torch.empty(n + PLANE_PAD, c, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(n + PLANE_PAD, c, dtype=torch.bfloat16, device=x.device) if _PRECISION == 3 else None
+    hi = torch.empty(n, c, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(n, c, dtype=torch.bfloat16, device=x.device) if _PRECISION == 3 else None
     call("pasco_split_planes", ptr(x), n, c, 0, ptr(scale), ptr(shift), act, ptr(hi), ptr(lo))
     return hi, lo
+
+
+def _planes_ok(c_contract: int, kk: int, nbr) -> bool:
+    return _USE_PLANES and nbr is not None and kk > 1 and c_contract % 64 == 0
 
 
 def _tc_ok(c_contract: int, c_out: int, K: int, kind: str = "fwd") -> bool:
@@ -380,10 +380,12 @@ def _tc_ok(c_contract: int, c_out: int, K: int, kind: str = "fwd") -> bool:
 def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor], n_out: int,
                transpose_w: bool, koff: Optional[Sequence[int]], bias: Optional[torch.Tensor] = None,
                in_scale=None, in_shift=None, in_act: int = 0, packs: Optional[PackedWeights] = None,
-               want_stats: bool = False) -> torch.Tensor:
+               want_stats: bool = False, planes=None, planes_out: Optional[list] = None) -> torch.Tensor:
     """out[o] = Σ_k act(feats·scale+shift)[nbr[k,o]] @ Wk, Wk = W[koff[k]] (transposed when transpose_w).
     want_stats: the kernel's epilogue also accumulates the column sums / sums of squares of `out` (the training-mode
-    BatchNorm statistics of the layer that follows) and leaves them for BatchNormAct (see take_pending_stats)."""
+    BatchNorm statistics of the layer that follows) and leaves them for BatchNormAct (see take_pending_stats).
+    planes: (hi, lo) bf16 planes of act(feats·scale+shift) if the caller already has them; planes_out: a list that
+    receives the planes this call made (the backward pass reuses them for the weight gradient)."""
     K, Cin, Cout = weight.shape
     c_contract, c_out = (Cout, Cin) if transpose_w else (Cin, Cout)
     assert feats.shape[1] == c_contract
@@ -398,10 +400,19 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
     global _PENDING_STATS
     _PENDING_STATS = None            # statistics of an earlier launch never survive another convolution
     use_tc = _tc_ok(c_contract, c_out, kk, "dgrad" if transpose_w else "fwd")
-    if use_tc and _USE_PLANES:
-        hi, lo = split_planes(feats, in_scale, in_shift, in_act)
+    split_k = use_tc and _SPLIT_K and load().pasco_conv_splitk_workspace_bytes(kk, n_out, c_out) > 0
+    if use_tc and not split_k and _planes_ok(c_contract, kk, nbr):
+        hi, lo = planes if planes is not None else split_planes(feats, in_scale, in_shift, in_act)
+        if planes_out is not None:
+            planes_out.append((hi, lo))
+        stats = None
+        if want_stats and _FUSE_BN_STATS and n_out >= 4096:
+            stats = torch.zeros(2, c_out, dtype=torch.float64, device=feats.device)
         call("pasco_conv_forward_planes", ptr(hi), ptr(lo), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
-             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(out), _PRECISION, 0)
+             ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(stats), ptr(out),
+             _PRECISION, 0, 0)
+        if stats is not None:
+            _PENDING_STATS = (weakref.ref(out), out.data_ptr(), out._version, tuple(out.shape), stats)
     elif use_tc and _SPLIT_K and (ws_bytes := load().pasco_conv_splitk_workspace_bytes(kk, n_out, c_out)) > 0:
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=feats.device)
         call("pasco_conv_forward_splitk", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
@@ -458,7 +469,9 @@ def fuse_bn_stats(flag: bool) -> None:
 
 
 def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tensor], K: int, Cin: int, Cout: int,
-               in_scale=None, in_shift=None, in_act: int = 0) -> torch.Tensor:
+               in_scale=None, in_shift=None, in_act: int = 0, in_planes=None, g_planes=None) -> torch.Tensor:
+    """in_planes / g_planes: (hi, lo) bf16 planes of act(feats·scale+shift) and of gout when the caller has them
+    (the forward pass made the former, the input-gradient launch of the same backward the latter)."""
     n_out = gout.shape[0]
     dW = torch.zeros(K, Cin, Cout, dtype=torch.float32, device=feats.device)
     feats, gout = feats.contiguous(), gout.contiguous()
@@ -466,7 +479,13 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if _tc_ok(Cin, 64, 1, "wgrad") and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256:
+    tc = _tc_ok(Cin, 64, 1, "wgrad") and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256
+    if tc and _planes_ok(Cin, K, nbr):
+        ih, il = in_planes if in_planes is not None else split_planes(feats, in_scale, in_shift, in_act)
+        gh, gl = g_planes if g_planes is not None else split_planes(gout)
+        call("pasco_conv_wgrad_planes", ptr(ih), ptr(il), feats.shape[0], ptr(nbr), K, n_out, Cin, Cout, ptr(gh), ptr(gl),
+             ptr(dW), _PRECISION, 0, 0)
+    elif tc:
         call("pasco_conv_wgrad_tc", ptr(feats), feats.shape[0], ptr(nbr), K, n_out, Cin, Cout, ptr(gout),
              ptr(in_scale), ptr(in_shift), in_act, ptr(dW), _PRECISION, 0, 0)
     else:
@@ -491,22 +510,39 @@ class SparseConv(torch.autograd.Function):
         ctx.kmap = kmap
         ctx.packs = packs
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(feats, weight)
-        return conv_apply(feats, weight, kmap.nbr, kmap.n_out, False, None,
-                          bias.view(-1).contiguous() if bias is not None else None, packs=packs, want_stats=True)
+        made = []
+        out = conv_apply(feats, weight, kmap.nbr, kmap.n_out, False, None,
+                         bias.view(-1).contiguous() if bias is not None else None, packs=packs, want_stats=True,
+                         planes_out=made)
+        # the weight gradient gathers the same rows: keep the planes the forward made instead of splitting again
+        ctx.n_planes = 0
+        if made and weight.requires_grad:
+            hi, lo = made[0]
+            ctx.n_planes = 1 if lo is None else 2
+            ctx.save_for_backward(feats, weight, *([hi] if lo is None else [hi, lo]))
+        else:
+            ctx.save_for_backward(feats, weight)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        feats, weight = ctx.saved_tensors
+        feats, weight = ctx.saved_tensors[:2]
+        in_planes = None
+        if ctx.n_planes:
+            in_planes = (ctx.saved_tensors[2], ctx.saved_tensors[3] if ctx.n_planes == 2 else None)
         kmap: KernelMap = ctx.kmap
         g = g.contiguous()
         gin = gw = gb = None
+        K, Cin, Cout = weight.shape
+        g_planes = None
+        if _planes_ok(Cout, K, kmap.nbr) and _tc_ok(Cout, Cin, K, "dgrad") and \
+                (ctx.needs_input_grad[0] and ctx.needs_input_grad[1]):
+            g_planes = split_planes(g)          # one split of the output gradient serves dgrad (gather) and wgrad (B operand)
         if ctx.needs_input_grad[0]:
             nbr_t, koff_t = kmap.transposed()
-            gin = conv_apply(g, weight, nbr_t, kmap.n_in, True, koff_t, packs=ctx.packs)
+            gin = conv_apply(g, weight, nbr_t, kmap.n_in, True, koff_t, packs=ctx.packs, planes=g_planes)
         if ctx.needs_input_grad[1]:
-            K, Cin, Cout = weight.shape
-            gw = conv_wgrad(feats, g, kmap.nbr, K, Cin, Cout)
+            gw = conv_wgrad(feats, g, kmap.nbr, K, Cin, Cout, in_planes=in_planes, g_planes=g_planes)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0, keepdim=True)
         return gin, gw, gb, None, None

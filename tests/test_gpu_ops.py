@@ -225,16 +225,60 @@ def test_conv_cuda_core_path(ME, kind, cin, cout):
         ops.force_simt(False)
 
 
-@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 256, 256), ("down", 64, 128), ("up", 128, 64)])
-def test_conv_presplit_plane_path(ME, kind, cin, cout):
-    """Optional producer variant (conv_planes.cu): activations pre-split into bf16 planes, cp.async gather."""
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 128, 128), ("k3", 256, 256), ("down", 64, 128),
+                                           ("up", 128, 64), ("k3", 64, 128)])
+def test_conv_register_gather_path(ME, kind, cin, cout):
+    """The round-1 kernels (k_conv_tc / k_wgrad_tc: fp32 rows gathered through registers, converted per offset) stay
+    available as ops.use_planes(False); the default since round 2 is the plane-gather path the tests above ran."""
     from pasco_b200 import ops
     ops.set_precision("fp32")
-    ops.use_planes(True)
+    ops.use_planes(False)
     try:
-        _run_conv_case(ME, kind, cin, cout, TOL_TIGHT)
+        _run_conv_case(ME, kind, cin, cout, TOL_TIGHT, bias=(cin == 64 and cout == 64))
     finally:
-        ops.use_planes(False)
+        ops.use_planes(True)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 64), (256, 256)])
+def test_conv_plane_and_register_gather_are_bit_identical(prec, cin, cout):
+    """Same operand split (x = hi + lo done once per tensor vs once per gathered copy), same MMA order and epilogue →
+    k_conv_pl and k_conv_tc must agree bit for bit: forward with bias + fused statistics, input gradient with mirrored
+    offsets, ragged last tile, ~40 % missing neighbours (zero-fill copies)."""
+    from pasco_b200 import ops
+    ops.set_precision(prec)
+    g = torch.Generator().manual_seed(4)
+    occ = torch.rand(48, 40, 14, generator=g) < 0.35
+    c = torch.nonzero(occ).int()
+    C = torch.cat([torch.zeros(c.shape[0], 1, dtype=torch.int32), c], 1).cuda()
+    N = C.shape[0]
+    assert N % 128 != 0 and N > 4096
+    table, _ = ops.hash_insert(C)
+    nbr = ops.kernel_map_probe(C, table, 3, (1, 1, 1))
+    F = torch.randn(N, cin, generator=g).cuda()
+    G = torch.randn(N, cout, generator=g).cuda()
+    W = (torch.randn(27, cin, cout, generator=g) * 0.05).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    koff = [26 - k for k in range(27)]
+    res = []
+    ops.split_k(False)
+    try:
+        for flag in (True, False):
+            ops.use_planes(flag)
+            pk = ops.PackedWeights()
+            f = ops.conv_apply(F, W, nbr, N, False, None, b, packs=pk, want_stats=True)
+            st = ops.take_pending_stats(f)
+            d = ops.conv_apply(G, W, nbr, N, True, koff, packs=pk)
+            w = ops.conv_wgrad(F, G, nbr, 27, cin, cout)
+            res.append((f, st, d, w))
+    finally:
+        ops.use_planes(True)
+        ops.split_k(True)
+        ops.set_precision("fp32")
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][2], res[1][2])
+    assert res[0][1] is not None and relerr(res[0][1], res[1][1]) <= 1e-12
+    assert relerr(res[0][3], res[1][3]) <= 1e-5          # dW: fp32 atomics, order differs
+    assert res[0][0].abs().sum() > 0
 
 
 @pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 128, 128), ("down", 64, 128), ("up", 128, 64)])
@@ -243,10 +287,12 @@ def test_conv_tma_gather_variant(ME, kind, cin, cout):
     from pasco_b200 import ops
     ops.set_precision("fp32")
     ops.set_conv_variant(1)
+    ops.use_planes(False)
     try:
         _run_conv_case(ME, kind, cin, cout, TOL_TIGHT)
     finally:
         ops.set_conv_variant(0)
+        ops.use_planes(True)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -267,6 +313,7 @@ def test_conv_tma_and_register_gather_are_bit_identical(prec):
     W = (torch.randn(27, 64, 128, generator=g) * 0.05).cuda()
     scale, shift = torch.rand(64, generator=g).cuda() + 0.5, torch.randn(64, generator=g).cuda()
     outs = []
+    ops.use_planes(False)
     try:
         for variant in (1, 0):
             ops.set_conv_variant(variant)
@@ -276,6 +323,7 @@ def test_conv_tma_and_register_gather_are_bit_identical(prec):
             outs.append((a, b))
     finally:
         ops.set_conv_variant(0)
+        ops.use_planes(True)
         ops.set_precision("fp32")
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert outs[0][0].abs().sum() > 0
@@ -364,6 +412,44 @@ def test_conv_many_tiles_per_cta(ME):
     ops.set_precision("fp32")
     e = _run_conv_case(ME, "k3", 64, 64, TOL_TIGHT, shape=(64, 64, 32), p=0.225)
     print(f"bf16x3 k3 64->64 @59k rows: fwd {e[0]:.2e} dgrad {e[1]:.2e} wgrad {e[2]:.2e}")
+
+
+def test_conv_benchmark_scale_rows_match_fp64():
+    """The largest layer shape of the benchmark (≈1 M rows, C = 64, K = 27, ~17 M pairs): forward, input gradient and
+    weight gradient of the plane-gather kernels against an fp64 evaluation on a 1/64 row subsample (forward / dgrad) and
+    the full fp64 contraction for two offsets (wgrad) — every persistent CTA walks ~56 tile groups here."""
+    from pasco_b200 import ops
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(9)
+    occ = torch.rand(256, 256, 32, generator=g) < 0.5
+    c = torch.nonzero(occ).int()
+    C = torch.cat([torch.zeros(c.shape[0], 1, dtype=torch.int32), c], 1).cuda()
+    N = C.shape[0]
+    assert N > 1_000_000
+    table, _ = ops.hash_insert(C)
+    nbr = ops.kernel_map_probe(C, table, 3, (1, 1, 1))
+    F = torch.randn(N, 64, generator=g).cuda()
+    G = torch.randn(N, 64, generator=g).cuda()
+    W = (torch.randn(27, 64, 64, generator=g) * 0.05).cuda()
+    koff = [26 - k for k in range(27)]
+    out = ops.conv_apply(F, W, nbr, N, False, None)
+    din = ops.conv_apply(G, W, nbr, N, True, koff)
+    dW = ops.conv_wgrad(F, G, nbr, 27, 64, 64)
+    rows = torch.arange(0, N, 64, device="cuda")
+    ref_f = torch.zeros(rows.numel(), 64, dtype=torch.float64, device="cuda")
+    ref_d = torch.zeros_like(ref_f)
+    Fd, Gd, Wd = F.double(), G.double(), W.double()
+    for k in range(27):
+        src = nbr[k][rows].long()
+        ok = src >= 0
+        ref_f[ok] += Fd[src[ok]] @ Wd[k]
+        ref_d[ok] += Gd[src[ok]] @ Wd[koff[k]].t()
+    assert relerr(out[rows], ref_f) <= TOL_TIGHT and relerr(din[rows], ref_d) <= TOL_TIGHT
+    for k in (0, 13):
+        src = nbr[k].long()
+        ok = src >= 0
+        ref_w = Fd[src[ok]].t() @ Gd[ok]
+        assert relerr(dW[k], ref_w) <= TOL_TIGHT, k
 
 
 def test_conv_tile_tail_and_single_voxel(ME):

@@ -71,21 +71,30 @@ def main():
             W = torch.randn(27, ch, ch, device=dev) * 0.05
             G = torch.randn(N, ch, device=dev)
             pk = ops.PackedWeights()
+            koff = [26 - k for k in range(27)]
             for prec in ("fp32", "bf16"):
                 ops.set_precision(prec)
                 ops.use_planes(True)
                 split = timed(lambda: ops.split_planes(F), flush=flush)
-                fwd_planes = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk), flush=flush)
+                fp, gp = ops.split_planes(F), ops.split_planes(G)
+                fwd_pl = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk, planes=fp), flush=flush)
+                dgr_pl = timed(lambda: ops.conv_apply(G, W, nbr, N, True, koff, packs=pk, planes=gp), flush=flush)
+                wgr_pl = timed(lambda: ops.conv_wgrad(F, G, nbr, 27, ch, ch, in_planes=fp, g_planes=gp), flush=flush)
                 ops.use_planes(False)
                 fwd = timed(lambda: ops.conv_apply(F, W, nbr, N, False, None, packs=pk), flush=flush)
-                dgr = timed(lambda: ops.conv_apply(G, W, nbr, N, True, [26 - k for k in range(27)], packs=pk), flush=flush)
+                dgr = timed(lambda: ops.conv_apply(G, W, nbr, N, True, koff, packs=pk), flush=flush)
                 wgr = timed(lambda: ops.conv_wgrad(F, G, nbr, 27, ch, ch), flush=flush)
+                ops.use_planes(True)
                 flops = 2.0 * pairs * ch * ch
-                dense_flops = 2.0 * N * 27 * ch * ch
-                bytes_min = 4.0 * (2 * N * ch) + 4.0 * 27 * ch * ch + 4.0 * 27 * N
-                emit(kind="conv3", occ=occ, N=N, C=ch, precision=prec, fwd_ms=fwd, fwd_planes_ms=fwd_planes, split_ms=split, dgrad_ms=dgr, wgrad_ms=wgr,
-                     fwd_useful_TFLOPs=flops / fwd / 1e9, fwd_issued_TFLOPs=dense_flops / fwd / 1e9 * (3 if prec == "fp32" else 1),
-                     fwd_alg_GBs=bytes_min / fwd / 1e6, wgrad_useful_TFLOPs=flops / wgr / 1e9)
+                issued = 2.0 * N * 27 * ch * ch * (3 if prec == "fp32" else 1)
+                bytes_min = 4.0 * (2 * N * ch) + 4.0 * 27 * ch * ch + 8.0 * pairs
+                emit(kind="conv3", occ=occ, N=N, C=ch, pairs=pairs, precision=prec, split_ms=split,
+                     fwd_planes_ms=fwd_pl, dgrad_planes_ms=dgr_pl, wgrad_planes_ms=wgr_pl,
+                     fwd_regs_ms=fwd, dgrad_regs_ms=dgr, wgrad_regs_ms=wgr,
+                     fwd_planes_useful_TFLOPs=flops / fwd_pl / 1e9, fwd_planes_issued_TFLOPs=issued / fwd_pl / 1e9,
+                     wgrad_planes_useful_TFLOPs=flops / wgr_pl / 1e9, wgrad_planes_issued_TFLOPs=issued / wgr_pl / 1e9,
+                     fwd_planes_alg_GBs=bytes_min / fwd_pl / 1e6, wgrad_planes_alg_GBs=bytes_min / wgr_pl / 1e6,
+                     gather_GBs=pairs * ch * (4 if prec == "fp32" else 2) / fwd_pl / 1e6)
             ops.set_precision("fp32")
             if N <= 300000 and ch == 64:
                 ops.force_simt(True)
