@@ -7,7 +7,7 @@
 
 One "step" = one pass of the hot path over one synthetic scene per GPU: point voxeliser → Net3D sparse
 U-Net → mask transformer (M=1, f=64, 100 queries, train-mode BatchNorm, decoder caps active) → losses →
-backward → (N>1: one flat NCCL all-reduce of the gradients) → fused AdamW step.  Weak scaling: one scene
+backward (N>1: gradient buckets all-reduced over NCCL while it runs) → fused AdamW step.  Weak scaling: one scene
 per GPU per step, `value` = N·K scenes ÷ max-over-ranks device time.
 
 Two timed regions, both bracketed by barrier + cuda.synchronize and CUDA events:
@@ -48,6 +48,9 @@ def log(msg):
 
 GRID, OCC, IN_CH, N_CLASSES = (256, 256, 32), 0.10, 283, 20
 METRIC = "scenes/sec (256x256x32 voxels @10% occ) fwd+bwd"
+# --shape: the two dataset shapes of BASELINE.json's configs (SemanticKITTI: net_panoptic_sparse.py:51; KITTI-360:
+# train_kitti360.py:115,152 — 19 classes, 8-wide point features, 8 % occupancy in configs[4])
+SHAPES = {"semkitti": dict(occ=0.10, in_ch=283, n_classes=20), "kitti360": dict(occ=0.08, in_ch=8, n_classes=19)}
 
 
 def _peaks():
@@ -179,9 +182,13 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(a.precision)
+    shp = SHAPES[a.shape]
+    OCC, IN_CH, N_CLASSES = shp["occ"], shp["in_ch"], shp["n_classes"]
+    M, ACC = a.m, max(1, a.accum)
 
     torch.manual_seed(0)
-    net = PascoNet(n_classes=N_CLASSES, n_infers=1, in_channels=IN_CH, f=64, num_queries=100).to(dev).train()
+    net = PascoNet(n_classes=N_CLASSES, n_infers=M, in_channels=IN_CH, f=64, num_queries=100,
+                   heavy_decoder=a.heavy_decoder).to(dev).train()
     if world > 1:
         n_sync = parallel.enable_sync_batchnorm(net)     # Trainer(sync_batchnorm=True), scripts/train.py:216
         log(f"SyncBatchNorm on {n_sync} fused BN layers")
@@ -189,37 +196,49 @@ def run_ours(a):
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4, fused=True)
     # every scene of the pool is seen by a warm-up step, so that the caching allocator holds blocks of every size before
     # the timed regions (a first-touch cudaMalloc synchronises the device)
-    n_pool = max(1, min(a.pool, a.warmup))
-    host_scenes = [pin(make_scene(GRID, OCC, 1, IN_CH, N_CLASSES, seed=sd)) for sd in parallel.scene_seeds(rank, world, n_pool)]
+    n_pool = max(1, min(a.pool, a.warmup * ACC))
+    host_scenes = [pin(make_scene(GRID, OCC, M, IN_CH, N_CLASSES, seed=sd)) for sd in parallel.scene_seeds(rank, world, n_pool)]
     dev_scenes = [to_device(s, dev) for s in host_scenes]
     torch.cuda.synchronize()
-    flat_grad = None
+    # the reference's DDP gradient averaging (scripts/train.py:213): 64 MB buckets all-reduced while backward continues
+    reducer = parallel.GradReducer(params, bucket_mb=a.bucket_mb) if world > 1 else None
 
-    def step(scene):
+    def step(scene, micro=0):
+        """One micro-step (one MIMO group of M scenes); the optimiser step closes on the last of ACC micro-steps
+        (gradient accumulation, scripts/train.py:62,203: `--accum_batch`)."""
         out = net(scene["in_feats"], scene["in_coords"], scene["global_min_Cs"], scene["global_max_Cs"],
                   scene["min_Cs"], scene["max_Cs"])
         loss = total_loss(out, scene, N_CLASSES, net.class_frequencies)
-        opt.zero_grad(set_to_none=True)
+        if ACC > 1:
+            loss = loss / ACC
+        last = micro == ACC - 1
+        if micro == 0:
+            if reducer is not None:
+                reducer.zero_grad()
+            else:
+                opt.zero_grad(set_to_none=True)
+        if reducer is not None and ACC > 1:
+            reducer.rearm(sync=last)
         loss.backward()
-        if world > 1:       # the reference's DDP gradient all-reduce (scripts/train.py:213), one flat NCCL call
-            nonlocal flat_grad
-            flat_grad = parallel.allreduce_gradients(params, bucket=flat_grad)
-        torch.nn.utils.clip_grad_norm_(params, 0.5)
-        opt.step()
+        if last:
+            if reducer is not None:
+                reducer.finish()
+            torch.nn.utils.clip_grad_norm_(params, 0.5)
+            opt.step()
         return loss
 
     copy_stream = torch.cuda.Stream(device=dev)
     loss_host = torch.zeros(max(a.steps, 1), dtype=torch.float32).pin_memory()
 
-    def timed(n_steps, from_host, profile_last=False):
+    def timed(n_steps, from_host):
         gc.collect()
         gc.disable()            # no collector pauses inside the timed region (collected between regions)
         try:
-            return _timed(n_steps, from_host, profile_last)
+            return _timed(n_steps, from_host)
         finally:
             gc.enable()
 
-    def _timed(n_steps, from_host, profile_last):
+    def _timed(n_steps, from_host):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -242,17 +261,17 @@ def run_ours(a):
                 return sc, ev
 
             nxt = prefetch(0)
-            for i in range(n_steps):
+            for i in range(n_steps * ACC):
                 sc, ev = nxt
                 main.wait_event(ev)
-                if i + 1 < n_steps:
+                if i + 1 < n_steps * ACC:
                     nxt = prefetch(i + 1)
-                loss_host[i % loss_host.shape[0]].copy_(step(sc).detach(), non_blocking=True)   # D2H read of the result
+                ls = step(sc, i % ACC).detach()
+                if i % ACC == ACC - 1:
+                    loss_host[(i // ACC) % loss_host.shape[0]].copy_(ls, non_blocking=True)   # D2H read of the result
         else:
-            for i in range(n_steps):
-                if profile_last and i == n_steps - 1:
-                    ops.PROFILE = []
-                last = step(dev_scenes[i % n_pool])
+            for i in range(n_steps * ACC):
+                last = step(dev_scenes[i % n_pool], i % ACC)
         e1.record()
         torch.cuda.synchronize()
         if from_host:
@@ -271,23 +290,18 @@ def run_ours(a):
     gc.collect()
     gc.freeze()
     log(f"model + {n_pool} scenes ready")
-    for i in range(a.warmup):
+    for i in range(a.warmup * ACC):
         faulthandler.dump_traceback_later(240, exit=False)
-        step(dev_scenes[i % n_pool])
+        step(dev_scenes[i % n_pool], i % ACC)
         torch.cuda.synchronize()
         faulthandler.cancel_dump_traceback_later()
         log(f"warm-up step {i} done, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    # per-launch CUDA events of the conv kernels (for the roofline block) are recorded during the LAST step of the timed
-    # region only: recording them for every step costs 5-20 ms/step of host time
     calls0 = ops.CALLS
-    ms, _ = timed(a.steps, from_host=False, profile_last=True)
+    ms, _ = timed(a.steps, from_host=False)
     launches = ops.CALLS - calls0
-    prof, ops.PROFILE = ops.PROFILE, None
-    prof_steps = 1
-    ops.PAIR_COUNTS.clear()
     log(f"device-resident region: {ms / a.steps:.1f} ms/step")
     # untimed: one pass of the input pipeline so that the copy stream's allocator pool holds blocks of every scene size
     # (a first-touch cudaMalloc inside the timed region would synchronise the device)
@@ -302,6 +316,16 @@ def run_ours(a):
     ms_e2e, _ = timed(a.steps, from_host=True)
     log(f"e2e region: {ms_e2e / a.steps:.1f} ms/step")
     clocks = sampler.stop() if sampler else None
+    # per-launch CUDA events of the conv kernels (the roofline block) come from ONE extra step of the same workload run
+    # right after the timed regions (same clocks, same allocator state): recording ~260 event pairs and the pair counts
+    # inside a timed region cost 5-20 ms/step of host time in round 1 and made `value` slower than `e2e`
+    ops.PROFILE = []
+    for j in range(ACC):
+        step(dev_scenes[(a.steps * ACC + j) % n_pool], j)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    prof_steps = 1
+    ops.PAIR_COUNTS.clear()
 
     # ---- roofline of the dominant kernel (per-launch CUDA-event durations recorded inside the timed region) ----
     groups = {}
@@ -338,20 +362,26 @@ def run_ours(a):
                 "hbm_achieved_GBs": round(ach_gb, 1), "hbm_frac": round(ach_gb / hbm_peak, 4),
                 "share_of_step": round(top["ms"] / (ms / a.steps * prof_steps), 3),
                 "all_conv_share_of_step": round(conv_ms / (ms / a.steps * prof_steps), 3),
-                "events": "per-launch CUDA events recorded during the last step of the timed region"}
+                "events": "per-launch CUDA events of one extra step run right after the timed regions (same workload)"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(world * a.steps / (ms / 1e3), 4), "unit": "scenes/s", "n_gpus": world,
+        scenes_per_step = world * ACC * M          # a MIMO group holds M scenes (one per subnet), ACC groups per optimiser step
+        default_mode = a.shape == "semkitti" and M == 1 and ACC == 1 and not a.heavy_decoder
+        workload = ("configs[1] shape: 256x256x32 @10% occ, full PaSCo (Net3D + MaskPLS 100 queries, M=1, f=64), "
+                    "fwd+bwd+AdamW, 1 scene/GPU/step, train-mode caps 25k/120k/400k") if default_mode else (
+            f"256x256x32 @{OCC:.0%} occ {a.shape} shape ({N_CLASSES} classes, {IN_CH}-wide point features), full PaSCo M={M}"
+            f"{' heavy decoder' if a.heavy_decoder else ''}, f=64, fwd+bwd+AdamW, {ACC} MIMO group(s) of {M} scene(s) per GPU per "
+            f"optimiser step (gradient accumulation), global batch {scenes_per_step} scenes")
+        line = {"metric": METRIC, "value": round(scenes_per_step * a.steps / (ms / 1e3), 4), "unit": "scenes/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core MMA, fp32 accumulate)"
                 if a.precision == "fp32" else "bf16 operands, fp32 accumulate", "data": "synthetic",
-                "config": {"workload": "configs[1] shape: 256x256x32 @10% occ, full PaSCo (Net3D + MaskPLS 100 queries, M=1, f=64), "
-                                       "fwd+bwd+AdamW, 1 scene/GPU/step, train-mode caps 25k/120k/400k",
+                "config": {"workload": workload, "global_batch": scenes_per_step, "accum": ACC, "n_infers": M, "shape": a.shape,
                            "loss": "CE+Lovasz completion @3 scales + Hungarian set loss (class CE, focal, dice, 3 aux levels)",
                            "parallelism": f"dp{world}", "l2": "inputs larger than L2: per-step working set (>4 GB of activations) >> 126 MB",
                            "scene_pool": n_pool, "random_init_weights": True},
-                "e2e": {"value": round(world * a.steps / (ms_e2e / 1e3), 4), "unit": "scenes/s",
-                        "h2d_bytes_per_step": h2d_bytes(host_scenes[0]), "d2h_bytes_per_step": 4,
+                "e2e": {"value": round(scenes_per_step * a.steps / (ms_e2e / 1e3), 4), "unit": "scenes/s",
+                        "h2d_bytes_per_step": h2d_bytes(host_scenes[0]) * ACC, "d2h_bytes_per_step": 4,
                         "ms_per_step": round(ms_e2e / a.steps, 3)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof}
         if world == 1 and not a.no_cpu_baseline:
@@ -362,41 +392,54 @@ def run_ours(a):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_baseline(budget_s: float = 20.0):
-    """CPU restatement of the ME algorithm (oracle/) on a bounded crop of the same workload, all host cores."""
+def cpu_baseline(_budget_s: float = 20.0):
+    """CPU restatement of the ME algorithm (oracle/) on THE fixed crop of the same workload (net_oracle.CROP_GRID, the same
+    crop `--impl reference` times), all host cores: 1 warm-up + 3 timed passes, median and spread."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import net_oracle
     cores = min(os.cpu_count(), 32)     # the per-offset gather/GEMM/scatter loop stops scaling beyond ~32 threads
     torch.set_num_threads(cores)
     log(f"cpu baseline on {cores} threads ...")
-    r = net_oracle.time_crop(budget_s)
-    return {"value": r["scenes_per_s"], "unit": "scenes/s", "cores": cores, "kind": "port",
-            "sample": r["sample"], "seconds": r["seconds"],
+    r = net_oracle.time_crop(repeats=3, warmup=1)
+    return {"value": round(r["scenes_per_s"], 6), "unit": "scenes/s", "cores": cores, "kind": "port",
+            "sample": r["sample"], "seconds_per_sample": r["seconds"], "times": r["times"], "spread": r["spread"],
             "note": "CPU restatement of the MinkowskiEngine 0.5.4 algorithm (ME not installable offline)"}
 
 
 def run_reference(a):
+    """The reference arm: the CPU restatement of the reference's MinkowskiEngine path on the host cores.  One STEP = one
+    forward+backward(+losses) pass over the fixed 1/16-scene crop (a bounded sample of config.workload); W warm-up and K
+    timed steps as asked (K is cut only if the run would exceed ~4 minutes; `steps` then reports what ran).
+    value = (1/16 scene) / median step time — the linear-in-voxels scaling is stated in config.workload;
+    `--ref-full-scene` adds ONE unscaled full-scene pass (minutes) as `full_scene`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = max(a.steps, 1), a.warmup
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import net_oracle
     cores = min(os.cpu_count(), 32)
     torch.set_num_threads(cores)
-    per = max(2.0, min(20.0, 120.0 / (steps + warm)))
-    for _ in range(min(warm, 1)):
-        net_oracle.time_crop(per)
-    rs = [net_oracle.time_crop(per) for _ in range(min(steps, 3))]
-    v = sum(r["scenes_per_s"] for r in rs) / len(rs)
+    t0 = time.time()
+    n_warm = max(1, min(a.warmup, 2))
+    probe = net_oracle.time_crop(repeats=1, warmup=n_warm)
+    per = probe["seconds"]
+    k_run = int(max(3, min(max(1, a.steps), (240.0 - (time.time() - t0)) / max(per, 1e-3))))
+    r = net_oracle.time_crop(repeats=k_run, warmup=0)
+    v = r["scenes_per_s"]
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": "scenes/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True,
+            "steps": k_run, "steps_requested": a.steps, "warmup": n_warm,
+            "ms_per_step": round(r["seconds"] * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1] shape: 256x256x32 @10% occ, full PaSCo fwd+bwd (M=1, f=64), CPU crop scaled to a full scene",
-                       "parallelism": "cpu"},
+            "config": {"workload": "configs[1] shape: 256x256x32 @10% occ, full PaSCo fwd+bwd+losses (M=1, f=64); each STEP is a "
+                                   "bounded sample = one 64x64x32 crop (1/16 scene, caps scaled 1/16); value = 1/(16 x median "
+                                   "step time), assuming cost linear in voxels",
+                       "parallelism": f"cpu x{cores} threads", "scene_fraction_per_step": 1.0 / r["div"]},
             "cpu_baseline": {"value": round(v, 6), "unit": "scenes/s", "cores": cores, "kind": "port",
-                             "sample": rs[0]["sample"]},
+                             "sample": r["sample"], "times": r["times"], "spread": r["spread"]},
             "e2e": {"value": round(v, 6), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if a.ref_full_scene:
+        f = net_oracle.time_full_scene()
+        line["full_scene"] = {"value": round(f["scenes_per_s"], 6), "unit": "scenes/s", "seconds": f["seconds"], "sample": f["sample"]}
     print(json.dumps(line), flush=True)
 
 
@@ -408,8 +451,14 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic scenes cycled through")
+    ap.add_argument("--shape", default="semkitti", choices=sorted(SHAPES), help="dataset shape (classes / point-feature width / occupancy)")
+    ap.add_argument("--m", type=int, default=1, help="MIMO subnets per network (n_infers); a step then covers M scenes per group")
+    ap.add_argument("--accum", type=int, default=1, help="MIMO groups per GPU per optimiser step (gradient accumulation)")
+    ap.add_argument("--heavy-decoder", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient all-reduce bucket size (N > 1)")
+    ap.add_argument("--ref-full-scene", action="store_true", help="--impl reference: also time one unscaled full scene")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

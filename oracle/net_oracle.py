@@ -215,30 +215,46 @@ class OracleNet(nn.Module):
         return {"sem_logits_at_scales": sem, "panop_predictions": [pred]}
 
 
-def time_crop(budget_s: float = 20.0, full_grid=(256, 256, 32), occ=0.10):
-    """Forward + backward (+ losses) of the CPU restatement on a crop of the benchmark scene sized for
-    ~budget_s seconds; returns scenes/s scaled to a full scene (crop voxels / full voxels)."""
+CROP_GRID, CROP_DIV = (64, 64, 32), 16      # THE bounded sample of the benchmark scene: 1/16 of 256x256x32, caps scaled 1/16
+
+
+def time_crop(repeats: int = 3, warmup: int = 1, occ=0.10, grid=CROP_GRID, div=CROP_DIV):
+    """Forward + backward (+ losses) of the CPU restatement on ONE fixed crop of the benchmark scene (the same crop for
+    bench.py's cpu_baseline leg and for --impl reference): `warmup` untimed passes, then `repeats` timed passes.
+    Returns the median time, the spread and scenes/s scaled to a full scene under the stated assumption that the cost is
+    linear in the voxel count (the crop keeps the occupancy, the z extent and the cap-to-voxel ratio of the full scene)."""
     from pasco_b200.synthetic import make_scene
     from pasco_b200.losses import total_loss
-    # ~7 s per 1/64 scene fwd+bwd+losses on 8 cores measured in the build container: choose the crop from the budget
-    options = [((32, 32, 32), 64), ((64, 32, 32), 32), ((64, 64, 32), 16), ((128, 64, 32), 8)]
-    grid, div = options[0]
-    for g, d in options:
-        if 450.0 / d * max(0.5, 8.0 / max(torch.get_num_threads(), 1)) <= budget_s:
-            grid, div = g, d
     torch.manual_seed(0)
     net = OracleNet(caps=tuple(max(8, c // div) for c in (25000, 120000, 400000))).train()
     scene = make_scene(grid, occ, 1, seed=0)
     freq = {f"1_{s}": np.ones(20) for s in (1, 2, 4)}
-    t0 = time.time()
-    out = net(scene)
-    loss = total_loss(out, scene, 20, freq)
-    loss.backward()
-    dt = time.time() - t0
-    return {"scenes_per_s": (1.0 / div) / dt, "seconds": round(dt, 2),
-            "sample": f"{grid[0]}x{grid[1]}x{grid[2]} crop (1/{div} of a scene) @ {occ:.0%} occ, fwd+bwd+losses, caps scaled 1/{div}"}
+    times = []
+    for i in range(warmup + repeats):
+        for q in net.parameters():
+            q.grad = None
+        t0 = time.time()
+        out = net(scene)
+        loss = total_loss(out, scene, 20, freq)
+        loss.backward()
+        if i >= warmup:
+            times.append(time.time() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"scenes_per_s": (1.0 / div) / med, "seconds": round(med, 3), "times": [round(t, 3) for t in times],
+            "spread": round((times[-1] - times[0]) / med, 3), "div": div,
+            "sample": f"{grid[0]}x{grid[1]}x{grid[2]} crop (1/{div} of a scene) @ {occ:.0%} occ, fwd+bwd+losses, caps scaled "
+                      f"1/{div}; {warmup} warm-up + {repeats} timed passes, median; scaled to a full scene assuming cost "
+                      f"linear in voxels"}
+
+
+def time_full_scene(occ=0.10):
+    """One full 256x256x32 scene forward + backward (+ losses), no scaling (minutes on 32 cores)."""
+    r = time_crop(repeats=1, warmup=0, occ=occ, grid=(256, 256, 32), div=1)
+    r["sample"] = f"one full 256x256x32 scene @ {occ:.0%} occ, fwd+bwd+losses, single un-warmed pass"
+    return r
 
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    print(time_crop(float(sys.argv[1]) if len(sys.argv) > 1 else 10.0))
+    print(time_full_scene() if "--full" in sys.argv else time_crop())

@@ -173,7 +173,7 @@ __device__ __forceinline__ void role_weight_loader(const ConvParams& p, const Pi
 }
 
 // one thread: tcgen05.mma (M=128, N=Cout, K=16) into the tile's TMEM accumulator; commits free the A / B ring slots
-template <int NSPLIT>
+template <int NSPLIT, bool CPASYNC_A = false>
 __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
   const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.Cout, 0, 0);
   int sa = 0, sb = 0;
@@ -193,6 +193,7 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
         const uint32_t b_hi = smem_u32(pl.b_smem + (size_t)sb * pl.b_stage_bytes), b_lo = b_hi + pl.b_tile;
         for (int t = 0; t < t_eff; ++t) {
           mbar_wait(smem_u32(pl.afull + sa), pa);
+          if (CPASYNC_A) fence_proxy_async_smem();   // the A stage was written by cp.async copies (generic proxy)
           tc_fence_after();
           const uint32_t a_hi = smem_u32(pl.a_smem + (size_t)sa * pl.a_stage_bytes), a_lo = a_hi + A_TILE_BYTES;
           const uint32_t d_tmem = pl.tmem_base + (uint32_t)(buf * pl.acc_cols + t * p.Cout);
@@ -842,22 +843,18 @@ __global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_co
 //   * a missing neighbour is a ZERO-FILL copy (src-size 0): no global or L2 traffic at all for the ~38 % of
 //     (row, offset) pairs that have no neighbour — the TMA gather4 variant of round 1 had to fetch a zero row for each;
 //   * 8 copies per lane per slot instead of ~600 gather/convert/store instructions.
-// Completion: one cp.async group per slot; a warp publishes slot n - pl_depth after cp.async.wait_group, a
-// generic→async proxy fence and one mbarrier arrive (same hand-off as the register kernel's st.shared path).
+// Completion is tracked by the hardware: after issuing the copies of a slot every producer thread executes
+// cp.async.mbarrier.arrive.noinc on the slot's "full" barrier (expected count = 256 producer threads), so the barrier
+// completes when the last copy has landed — no wait_group, no software publish step, and the producers run up to `sa`
+// slots ahead of the MMA (a first version published slot n-D in software after issuing slot n: ncu showed the MMA
+// thread and the producers waiting on each other's hand-off, 1.43 ms).  The MMA thread adds a generic→async proxy
+// fence after its barrier wait (CUTLASS's sm100 cp.async collective issues none; it costs one instruction per slot).
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups of this thread are pending
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    default: cp_async_wait<7>(); break;
-  }
+// the mbarrier receives one arrival from this thread once all its cp.async copies issued so far have completed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 template <int NSPLIT>
@@ -891,7 +888,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
     for (int i = threadIdx.x; i < 2 * p.Cout; i += NUM_THREADS) stat_acc[i] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(smem_u32(afull + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(afull + s), 32);   // one cp.async arrival per lane of the warp that fills the slot
       mbar_init(smem_u32(aempty + s), 1);
       mbar_init(smem_u32(bfull + s), 1);
       mbar_init(smem_u32(bempty + s), 1);
@@ -917,9 +914,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
 
   if (warp < NUM_GATHER_WARPS) {
     // ===================================== plane-gather producers =====================================
-    // Warp w owns tile rows 16w .. 16w+15.  One copy instruction moves 4 rows: lane = (row sub-index 0..3, 16-byte
-    // chunk 0..7 of the 128-byte row); 4 instructions per plane per slot.  Lane j < 16 holds the neighbour index of
-    // row 16w + j (one coalesced 64-byte load per slot, fetched PF slots ahead), distributed by shuffles.
+    // ONE WARP PER SLOT: warp w fills the slots n ≡ w (mod 8) of the CTA's slot sequence (work item → k → kb → tile),
+    // all 128 rows of the tile.  (A first version let every warp fill 16 rows of EVERY slot: ncu showed ~300
+    // instructions of per-slot bookkeeping per warp for 8 copies, 900 cycles per slot against 384 cycles of MMA.)
+    // One copy instruction moves 4 rows: lane = (row sub-index 0..3, 16-byte chunk 0..7 of the 128-byte row); 32
+    // instructions per plane per slot.  Lane l holds the neighbour indices of rows l, l+32, l+64, l+96 (four coalesced
+    // 128-byte loads, fetched two of the warp's slots = 16 CTA slots ahead), distributed by one shuffle per instruction.
     const int ch = lane & 7, sub = lane >> 3;
     const int64_t num_items = num_groups * p.ksplit;
     struct It {
@@ -947,73 +947,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
       if (++it.k < it.k1) return;
       enter(it, it.v + gridDim.x);
     };
-    auto load_idx = [&](const It& it) -> int {
-      int idx = -1;
-      if (it.valid && lane < ROWS_PER_WARP) {
-        const int64_t row = (it.group * T + it.t) * BLOCK_M + warp * ROWS_PER_WARP + lane;
-        if (row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)it.k * p.n_out + row) : (int)row;
+    auto advance_n = [&](It& it, int n) {
+      for (int i = 0; i < n && it.valid; ++i) advance(it);
+    };
+    struct Idx4 { int v[4]; };
+    auto load_idx = [&](const It& it) -> Idx4 {
+      Idx4 r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        r.v[j] = -1;
+        if (it.valid) {
+          const int64_t row = (it.group * T + it.t) * BLOCK_M + j * 32 + lane;
+          if (row < p.n_out) r.v[j] = p.nbr ? __ldg(p.nbr + (int64_t)it.k * p.n_out + row) : (int)row;
+        }
       }
-      return idx;
+      return r;
     };
-    constexpr int PF = 4;
-    It cur, pf;
-    enter(cur, blockIdx.x);
-    pf = cur;
-    int q[PF];
+    It it0, it1, it2;
+    enter(it0, blockIdx.x);
+    advance_n(it0, warp);
+    it1 = it0;
+    advance_n(it1, NUM_GATHER_WARPS);
+    it2 = it1;
+    advance_n(it2, NUM_GATHER_WARPS);
+    Idx4 q0 = load_idx(it0), q1 = load_idx(it1);
+    int n = warp;                                   // slot number in the CTA's sequence
+    const uint8_t* base_hi = reinterpret_cast<const uint8_t*>(p.pl_hi);
+    const uint8_t* base_lo = reinterpret_cast<const uint8_t*>(p.pl_lo);
+    const int64_t pitch_b = p.pl_pitch * 2;
+    while (it0.valid) {
+      const Idx4 q2 = load_idx(it2);                // indices of this warp's slot after next
+      const int stage = n % p.sa;
+      const uint32_t parity = (uint32_t)((n / p.sa) & 1);
+      mbar_wait(smem_u32(aempty + stage), parity ^ 1);
+      const uint32_t dst0 = smem_u32(a_smem + (size_t)stage * a_stage_bytes) + (uint32_t)sub * 128u;
+      const int64_t coff_b = ((int64_t)it0.kb * KBLK + ch * 8) * 2;
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      q[i] = load_idx(pf);
-      if (pf.valid) advance(pf);
-    }
-    const int D = p.pl_depth;
-    int stage = 0, astage = 0;        // next stage to fill / next stage to publish
-    uint32_t phase = 0;
-    int pending = 0;
-    auto publish_oldest = [&]() {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(afull + astage));
-      if (++astage == p.sa) astage = 0;
-      --pending;
-    };
-    while (cur.valid) {
-      const int myidx = q[0];
-#pragma unroll
-      for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
-      q[PF - 1] = load_idx(pf);
-      if (pf.valid) advance(pf);
-
-      mbar_wait(smem_u32(aempty + stage), phase ^ 1);
-      const uint32_t dst0 = smem_u32(a_smem + (size_t)stage * a_stage_bytes);
-      const int64_t coff = (int64_t)cur.kb * KBLK + ch * 8;
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_WARP / 4; ++i) {
-        const int r = warp * ROWS_PER_WARP + i * 4 + sub;
-        const int idx = __shfl_sync(0xffffffffu, myidx, i * 4 + sub);
+      for (int i = 0; i < 32; ++i) {
+        // tile row r = 4i + sub; its index lives in register (i / 8) of lane (4 (i % 8) + sub)
+        const int idx = __shfl_sync(0xffffffffu, q0.v[i >> 3], ((i & 7) << 2) + sub);
         const uint32_t nbytes = idx >= 0 ? 16u : 0u;
-        const int64_t eoff = (int64_t)(idx >= 0 ? idx : 0) * p.pl_pitch + coff;
-        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
-        cp_async16_zfill(dst0 + off, p.pl_hi + eoff, nbytes);
-        if (NSPLIT == 3) cp_async16_zfill(dst0 + A_TILE_BYTES + off, p.pl_lo + eoff, nbytes);
+        const int64_t boff = (int64_t)(idx >= 0 ? idx : 0) * pitch_b + coff_b;
+        // byte offset of (row r, chunk ch) in the swizzled tile: r*128 + ((ch ^ (r & 7)) << 4), r & 7 = 4 (i & 1) + sub
+        const uint32_t off = (uint32_t)i * 512u + (((uint32_t)ch ^ (((uint32_t)(i & 1) << 2) + (uint32_t)sub)) << 4);
+        cp_async16_zfill(dst0 + off, base_hi + boff, nbytes);
+        if (NSPLIT == 3) cp_async16_zfill(dst0 + A_TILE_BYTES + off, base_lo + boff, nbytes);
       }
-      cp_async_commit();
-      ++pending;
-      if (++stage == p.sa) {
-        stage = 0;
-        phase ^= 1;
-      }
-      advance(cur);
-      if (pending > D) {
-        cp_async_wait_dyn(D);
-        publish_oldest();
-      }
+      cp_async_mbar_arrive_noinc(smem_u32(afull + stage));
+      n += NUM_GATHER_WARPS;
+      it0 = it1; it1 = it2;
+      advance_n(it2, NUM_GATHER_WARPS);
+      q0 = q1; q1 = q2;
     }
+    cp_async_commit();
     cp_async_wait<0>();
-    while (pending > 0) publish_oldest();
   } else if (warp == LOAD_WARP) {
     if (lane == 0) role_weight_loader(p, pl);
   } else if (warp == MMA_WARP) {
-    if (lane == 0) role_mma<NSPLIT>(p, pl);
+    if (lane == 0) role_mma<NSPLIT, true>(p, pl);
   } else {
     role_epilogue(p, pl, warp - NUM_GATHER_WARPS, lane);
   }
@@ -1268,9 +1259,8 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   }
   p.pl_hi = (const uint16_t*)hi; p.pl_lo = (const uint16_t*)lo; p.pl_pitch = pitch;
   static const int depth_env = [] { const char* e = getenv("PASCO_PL_DEPTH"); return e ? atoi(e) : 0; }();
-  p.pl_depth = sa - 1;                       // all but one stage in flight; the MMA works on the remaining one
-  if (depth_env > 0 && depth_env < p.pl_depth) p.pl_depth = depth_env;
-  if (p.pl_depth > 7) p.pl_depth = 7;
+  p.pl_depth = sa;                           // informational: the producers may run `sa` slots ahead of the MMA
+  (void)depth_env;
   const size_t smem = (size_t)sa * a_stage + (size_t)sb * b_stage + fixed;
   const int64_t groups = (tiles + T - 1) / T;
   const int grid = (int)(groups < num_sms() ? groups : num_sms());

@@ -370,10 +370,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_tc(const __grid_consta
 // ------------------------------------------------------------------------------------------------------------
 // Same UMMA view, TMEM residency, passes and epilogue as k_wgrad_tc; the producers only move bytes: 16-byte cp.async
 // copies from the `in` planes (gathered rows; a missing neighbour is a zero-fill copy that touches no memory) and from
-// the `gout` planes (contiguous rows) straight into the 128-byte-swizzled tiles.  One cp.async group per slot
-// (slot 0 of a row tile = the whole gout tile, slots 1.. = one unit of two gathered sub-tiles each); a warp publishes
-// slot n - depth after cp.async.wait_group + a generic→async proxy fence.  Round-1 k_wgrad_tc spent ~600 gather /
-// convert / store instructions per sub-tile and ran at 15 % tensor-pipe utilisation, 2.4x slower than the forward.
+// the `gout` planes (contiguous rows) straight into the 128-byte-swizzled tiles.  Slot 0 of a row tile = the whole gout
+// tile, slots 1.. = one unit of two gathered sub-tiles each; every producer thread arrives on the slot's "full" barrier
+// with cp.async.mbarrier.arrive.noinc (count = 256 threads), so the hardware completes it when the last copy has landed
+// and the producers run a whole ring ahead of the MMA.  Round-1 k_wgrad_tc spent ~600 gather / convert / store
+// instructions per sub-tile and ran at 15 % tensor-pipe utilisation, 2.4x slower than the forward.
 struct WgradPlParams {
   const uint16_t* in_hi;
   const uint16_t* in_lo;
@@ -391,17 +392,8 @@ struct WgradPlParams {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    default: cp_async_wait<7>(); break;
-  }
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 template <int NSPLIT>
@@ -432,11 +424,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(full_bar + s), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(full_bar + s), 32);    // one cp.async arrival per lane of the warp that fills the slot
       mbar_init(smem_u32(empty_bar + s), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(gfull_bar + b), NUM_GATHER_WARPS);
+      mbar_init(smem_u32(gfull_bar + b), 32);
       mbar_init(smem_u32(gempty_bar + b), 1);
     }
     mbar_init(smem_u32(done_bar), 1);
@@ -450,104 +442,92 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
   const int spr = 1 + nunits;                // slots per row tile: the gout tile, then one per unit
 
   if (warp < NUM_GATHER_WARPS) {
-    // lane = (row sub-index 0..3, 16-byte chunk 0..7): one copy instruction moves 4 of the warp's 8 tile rows
+    // ONE WARP PER SLOT: the CTA's slot sequence is (row tile → [gout tile, unit 0, unit 1, ...]); warp w fills the slots
+    // s ≡ w (mod 8), every row of them.  lane = (row sub-index 0..3, 16-byte chunk 0..7): one copy instruction moves 4
+    // tile rows.  For a unit slot lane l holds the neighbour indices of rows l and l+32 of both sub-tiles (four coalesced
+    // 128-byte loads, fetched one of the warp's slots = 8 CTA slots ahead), distributed by one shuffle per instruction.
     const int ch = lane & 7, sub = lane >> 3;
     const int64_t stride_rt = p.ctas_per_pass;
-    // neighbour indices of a unit slot: lanes 0-7 = rows of sub-tile 0, lanes 8-15 = rows of sub-tile 1
-    auto load_idx = [&](int64_t rt, int j) -> int {
-      int idx = -1;
-      if (j > 0 && rt < num_rt && lane < 16) {
-        const int sb = (unit0 + (j - 1)) * 2 + (lane >> 3);
-        const int64_t row = rt * WG_R + warp * WROWS + (lane & 7);
-        if (sb < p.num_subs && row < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)(sb / CB) * p.n_out + row) : (int)row;
-      }
-      return idx;
-    };
-    constexpr int PF = 4;
-    int64_t c_rt = cta_in_pass, f_rt = cta_in_pass, a_rt = cta_in_pass;     // issue / index-prefetch / publish cursors
-    int c_j = 0, f_j = 0, a_j = 0;
-    int q[PF];
+    const int64_t my_rts = cta_in_pass < num_rt ? (num_rt - cta_in_pass + stride_rt - 1) / stride_rt : 0;   // row tiles of this CTA
+    const int64_t total_slots = my_rts * spr;
+    struct Idx4 { int v[4]; };                      // [sub-tile h][row half]
+    auto load_idx = [&](int64_t s) -> Idx4 {
+      Idx4 r;
+      r.v[0] = r.v[1] = r.v[2] = r.v[3] = -1;
+      if (s < total_slots) {
+        const int64_t rt = cta_in_pass + (s / spr) * stride_rt;
+        const int j = (int)(s % spr);
+        if (j > 0) {
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      q[i] = load_idx(f_rt, f_j);
-      if (++f_j == spr) { f_j = 0; f_rt += stride_rt; }
-    }
-    const int D = p.depth;
-    int stage = 0, astage = 0, git = 0, agit = 0, pending = 0;
-    uint32_t phase = 0;
-    auto publish_oldest = [&]() {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (a_j == 0) {
-        if (lane == 0) mbar_arrive(smem_u32(gfull_bar + (agit & 1)));
-        ++agit;
-      } else {
-        if (lane == 0) mbar_arrive(smem_u32(full_bar + astage));
-        if (++astage == p.stages) astage = 0;
-      }
-      if (++a_j == spr) { a_j = 0; a_rt += stride_rt; }
-      --pending;
-    };
-    while (c_rt < num_rt) {
-      const int myidx = q[0];
+          for (int h = 0; h < 2; ++h) {
+            const int sbi = (unit0 + (j - 1)) * 2 + h;
 #pragma unroll
-      for (int i = 0; i + 1 < PF; ++i) q[i] = q[i + 1];
-      q[PF - 1] = load_idx(f_rt, f_j);
-      if (++f_j == spr) { f_j = 0; f_rt += stride_rt; }
-
-      if (c_j == 0) {
-        // ---- the gout tile of this row tile: [64 rows][Cout] per plane, contiguous rows ----
-        const int gb = git & 1;
-        mbar_wait(smem_u32(gempty_bar + gb), ((git >> 1) & 1) ^ 1);
-        const uint32_t g0 = smem_u32(g_smem + (size_t)gb * g_bytes);
-#pragma unroll
-        for (int i = 0; i < WROWS / 4; ++i) {
-          const int r = warp * WROWS + i * 4 + sub;
-          const int64_t row = c_rt * WG_R + r;
-          const uint32_t nbytes = row < p.n_out ? 16u : 0u;
-          const int64_t eoff = (row < p.n_out ? row : 0) * p.gout_pitch + ch * 8;
-          const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
-          for (int nb = 0; nb < NB; ++nb) {
-            cp_async16_zfill(g0 + (uint32_t)nb * WG_SUB_BYTES + off, p.g_hi + eoff + nb * 64, nbytes);
-            if (NSPLIT == 3) cp_async16_zfill(g0 + (uint32_t)(NB + nb) * WG_SUB_BYTES + off, p.g_lo + eoff + nb * 64, nbytes);
+            for (int q = 0; q < 2; ++q) {
+              const int64_t row = rt * WG_R + q * 32 + lane;
+              if (sbi < p.num_subs && row < p.n_out)
+                r.v[h * 2 + q] = p.nbr ? __ldg(p.nbr + (int64_t)(sbi / CB) * p.n_out + row) : (int)row;
+            }
           }
         }
-        ++git;
+      }
+      return r;
+    };
+    const uint8_t* in_hi = reinterpret_cast<const uint8_t*>(p.in_hi);
+    const uint8_t* in_lo = reinterpret_cast<const uint8_t*>(p.in_lo);
+    const uint8_t* gp_hi = reinterpret_cast<const uint8_t*>(p.g_hi);
+    const uint8_t* gp_lo = reinterpret_cast<const uint8_t*>(p.g_lo);
+    int64_t s = warp;
+    Idx4 q0 = load_idx(s);
+    for (; s < total_slots; s += NUM_GATHER_WARPS) {
+      const Idx4 q1 = load_idx(s + NUM_GATHER_WARPS);
+      const int64_t rti = s / spr;
+      const int j = (int)(s - rti * spr);
+      const int64_t rt = cta_in_pass + rti * stride_rt;
+      if (j == 0) {
+        // ---- the gout tile of this row tile: [64 rows][Cout] per plane, contiguous rows ----
+        const int gb = (int)(rti & 1);
+        mbar_wait(smem_u32(gempty_bar + gb), (uint32_t)(((rti >> 1) & 1) ^ 1));
+        const uint32_t g0 = smem_u32(g_smem + (size_t)gb * g_bytes) + (uint32_t)sub * 128u;
+#pragma unroll 4
+        for (int i = 0; i < WG_R / 4; ++i) {
+          const int64_t row = rt * WG_R + i * 4 + sub;
+          const uint32_t nbytes = row < p.n_out ? 16u : 0u;
+          const int64_t boff = ((row < p.n_out ? row : 0) * p.gout_pitch + ch * 8) * 2;
+          const uint32_t off = (uint32_t)i * 512u + (((uint32_t)ch ^ (((uint32_t)(i & 1) << 2) + (uint32_t)sub)) << 4);
+          for (int nb = 0; nb < NB; ++nb) {
+            cp_async16_zfill(g0 + (uint32_t)nb * WG_SUB_BYTES + off, gp_hi + boff + nb * 128, nbytes);
+            if (NSPLIT == 3) cp_async16_zfill(g0 + (uint32_t)(NB + nb) * WG_SUB_BYTES + off, gp_lo + boff + nb * 128, nbytes);
+          }
+        }
+        cp_async_mbar_arrive_noinc(smem_u32(gfull_bar + gb));
       } else {
         // ---- one unit: two gathered [64 rows][64 ch] sub-tiles ----
-        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-        const uint32_t a0 = smem_u32(a_smem + (size_t)stage * a_bytes);
-        const int sb0 = (unit0 + (c_j - 1)) * 2;
+        const int64_t ord = rti * nunits + (j - 1);
+        const int stage = (int)(ord % p.stages);
+        const uint32_t parity = (uint32_t)((ord / p.stages) & 1);
+        mbar_wait(smem_u32(empty_bar + stage), parity ^ 1);
+        const uint32_t a0 = smem_u32(a_smem + (size_t)stage * a_bytes) + (uint32_t)sub * 128u;
+        const int sb0 = (unit0 + (j - 1)) * 2;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int sbi = sb0 + h;
-          const int cb = sbi < p.num_subs ? sbi % CB : 0;
+          const int64_t coff_b = ((int64_t)(sbi < p.num_subs ? sbi % CB : 0) * 64 + ch * 8) * 2;
 #pragma unroll
-          for (int i = 0; i < WROWS / 4; ++i) {
-            const int r = warp * WROWS + i * 4 + sub;
-            const int idx = __shfl_sync(0xffffffffu, myidx, h * 8 + i * 4 + sub);
+          for (int i = 0; i < WG_R / 4; ++i) {
+            const int idx = __shfl_sync(0xffffffffu, q0.v[h * 2 + (i >> 3)], ((i & 7) << 2) + sub);
             const uint32_t nbytes = idx >= 0 ? 16u : 0u;
-            const int64_t eoff = (int64_t)(idx >= 0 ? idx : 0) * p.in_pitch + cb * 64 + ch * 8;
-            const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
-            cp_async16_zfill(a0 + (uint32_t)h * WG_SUB_BYTES + off, p.in_hi + eoff, nbytes);
-            if (NSPLIT == 3) cp_async16_zfill(a0 + (uint32_t)(2 + h) * WG_SUB_BYTES + off, p.in_lo + eoff, nbytes);
+            const int64_t boff = (int64_t)(idx >= 0 ? idx : 0) * p.in_pitch * 2 + coff_b;
+            const uint32_t off = (uint32_t)i * 512u + (((uint32_t)ch ^ (((uint32_t)(i & 1) << 2) + (uint32_t)sub)) << 4);
+            cp_async16_zfill(a0 + (uint32_t)h * WG_SUB_BYTES + off, in_hi + boff, nbytes);
+            if (NSPLIT == 3) cp_async16_zfill(a0 + (uint32_t)(2 + h) * WG_SUB_BYTES + off, in_lo + boff, nbytes);
           }
         }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        cp_async_mbar_arrive_noinc(smem_u32(full_bar + stage));
       }
-      cp_async_commit();
-      ++pending;
-      if (++c_j == spr) { c_j = 0; c_rt += stride_rt; }
-      if (pending > D) {
-        cp_async_wait_dyn(D);
-        publish_oldest();
-      }
+      q0 = q1;
     }
+    cp_async_commit();
     cp_async_wait<0>();
-    while (pending > 0) publish_oldest();
     // epilogue (gather warps 0-3): once the CTA's last MMA has retired, add the partial dW
     if (warp < 4) {
       const int qd = warp;
@@ -583,11 +563,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
       for (int64_t rt = cta_in_pass; rt < num_rt; rt += p.ctas_per_pass, ++git) {
         const int gb = git & 1;
         mbar_wait(smem_u32(gfull_bar + gb), (git >> 1) & 1);
+        fence_proxy_async_smem();                  // tiles were written by cp.async copies (generic proxy)
         tc_fence_after();
         const uint32_t g_hi = smem_u32(g_smem + (size_t)gb * g_bytes);
         const uint32_t g_lo = g_hi + NB * WG_SUB_BYTES;
         for (int u = 0; u < nunits; ++u) {
           mbar_wait(smem_u32(full_bar + stage), phase);
+          fence_proxy_async_smem();
           tc_fence_after();
           const uint32_t a_hi = smem_u32(a_smem + (size_t)stage * a_bytes);
           const uint32_t a_lo = a_hi + 2 * WG_SUB_BYTES;

@@ -233,6 +233,30 @@ class TensorField:
     """Referenced only in isinstance checks (pasco/models/dropout.py:23,47)."""
 
 
+class _LazyRows:
+    """Deferred act(BatchNorm(x)) over rows — what MinkowskiBatchNorm (+ a following MinkowskiReLU / LeakyReLU) returns in
+    training mode.  If the consumer is a stride-1 k>1 MinkowskiConvolution the three run as ONE fused node whose
+    BatchNorm apply pass writes the bf16 planes the convolution gathers (ops.BNActConv); any other consumer reading `.F`
+    materialises it through the fused row kernels (ops.batchnorm_rows).  Results are identical either way; this only
+    removes one full read+write of the activations per BatchNorm → convolution pair of the UNMODIFIED reference model
+    (pre-activation residual blocks, pasco/maskpls/mink.py:618-658)."""
+    ndim = 2
+
+    def __init__(self, bn, x: torch.Tensor, act: int, group):
+        self.bn, self.x, self.act, self.group = bn, x, act, group
+        self.shape, self.device, self.dtype, self.is_cuda = x.shape, x.device, x.dtype, x.is_cuda
+        self.requires_grad = x.requires_grad or (bn.weight is not None and bn.weight.requires_grad)
+
+    def size(self, *a):
+        return self.x.size(*a)
+
+    def with_act(self, act: int) -> "_LazyRows":
+        return _LazyRows(self.bn, self.x, act, self.group)
+
+    def materialise(self) -> torch.Tensor:
+        return ops.batchnorm_rows(self.bn, self.x, self.act, self.group)
+
+
 class SparseTensor:
     """ME.SparseTensor(features, coordinates=None, tensor_stride=1, coordinate_map_key=None,
     coordinate_manager=None) — call sites: net_panoptic_sparse.py:323; unet3d_sparse_v2.py:207-212;
@@ -241,7 +265,7 @@ class SparseTensor:
     def __init__(self, features, coordinates=None, tensor_stride=1, coordinate_map_key=None,
                  coordinate_manager=None, quantization_mode=SparseTensorQuantizationMode.RANDOM_SUBSAMPLE,
                  allocator_type=None, minkowski_algorithm=None, requires_grad=None, device=None):
-        if not (isinstance(features, torch.Tensor) and features.ndim == 2):
+        if not (isinstance(features, (torch.Tensor, _LazyRows)) and features.ndim == 2):
             raise ValueError("features must be a [N, C] tensor")
         if coordinate_map_key is None:
             if coordinates is None:
@@ -265,10 +289,15 @@ class SparseTensor:
         self.coordinate_manager = coordinate_manager
         self.coordinate_map_key = coordinate_map_key
         if requires_grad is not None:
-            self._F.requires_grad_(requires_grad)
+            self.F.requires_grad_(requires_grad)
 
-    F = property(lambda self: self._F)
-    features = property(lambda self: self._F)
+    @property
+    def F(self) -> torch.Tensor:
+        if isinstance(self._F, _LazyRows):
+            self._F = self._F.materialise()
+        return self._F
+
+    features = F
     C = property(lambda self: self.coordinate_manager.get_coordinates(self.coordinate_map_key))
     coordinates = C
     tensor_stride = property(lambda self: list(self.coordinate_map_key.tensor_stride))
@@ -287,12 +316,15 @@ class SparseTensor:
     def __repr__(self):
         return f"SparseTensor(pasco_b200, F={tuple(self._F.shape)}, tensor_stride={self.tensor_stride})"
 
+    def _pending(self) -> Optional[_LazyRows]:
+        return self._F if isinstance(self._F, _LazyRows) else None
+
     # criterion_sparse.py:273-274
     def _rows_of_batch(self, b: int):
         return torch.nonzero(self.C[:, 0] == b, as_tuple=True)[0]
 
     def features_at(self, b: int):
-        return self._F[self._rows_of_batch(b)]
+        return self.F[self._rows_of_batch(b)]
 
     def coordinates_at(self, b: int):
         return self.C[self._rows_of_batch(b)][:, 1:]
@@ -328,7 +360,7 @@ class SparseTensor:
         if any(m % s for m, s in zip(mn_l, ts)):
             raise AssertionError("The minimum coordinates must be divisible by the tensor stride.")
         step = ts if contract_stride else [1, 1, 1]
-        nch = self._F.shape[1]
+        nch = self.F.shape[1]
         if shape is None:
             mx = C_[:, 1:].max(0)[0].tolist()
             size = [(int(m) - lo) // st + 1 for m, lo, st in zip(mx, mn_l, step)]
@@ -337,22 +369,22 @@ class SparseTensor:
             if len(shape) != 5 or int(shape[1]) != nch:
                 raise ValueError("shape must be [B, C, X, Y, Z] with C matching the features")
             shape = tuple(int(s) for s in shape)
-        dense = ops.ToDense.apply(self._F.float(), C_, tuple(mn_l), tuple(step), shape)
+        dense = ops.ToDense.apply(self.F.float(), C_, tuple(mn_l), tuple(step), shape)
         return dense, ret_min, torch.IntTensor(ts)
 
     # -- arithmetic: same key → elementwise, different keys → coordinate union (decoder_v3.py:163) --
     def _combine(self, other, sign: float):
         cm = self.coordinate_manager
         if not isinstance(other, SparseTensor):
-            return SparseTensor(self._F + sign * other, coordinate_map_key=self.coordinate_map_key, coordinate_manager=cm)
+            return SparseTensor(self.F + sign * other, coordinate_map_key=self.coordinate_map_key, coordinate_manager=cm)
         if other.coordinate_manager is not cm:
             raise ValueError("SparseTensors of different coordinate managers cannot be combined")
         if other.coordinate_map_key == self.coordinate_map_key:
-            return SparseTensor(self._F + sign * other._F, coordinate_map_key=self.coordinate_map_key,
+            return SparseTensor(self.F + sign * other.F, coordinate_map_key=self.coordinate_map_key,
                                 coordinate_manager=cm)
         out_key, rows_b, n_out = cm.union_map(self.coordinate_map_key, other.coordinate_map_key)
-        b = other._F if sign > 0 else -other._F
-        return SparseTensor(ops.UnionAdd.apply(self._F.float(), b.float(), rows_b, n_out),
+        b = other.F if sign > 0 else -other.F
+        return SparseTensor(ops.UnionAdd.apply(self.F.float(), b.float(), rows_b, n_out),
                             coordinate_map_key=out_key, coordinate_manager=cm)
 
     def __add__(self, other):
@@ -366,12 +398,12 @@ class SparseTensor:
     def __mul__(self, other):
         if isinstance(other, SparseTensor):
             assert other.coordinate_map_key == self.coordinate_map_key
-            other = other._F
-        return SparseTensor(self._F * other, coordinate_map_key=self.coordinate_map_key,
+            other = other.F
+        return SparseTensor(self.F * other, coordinate_map_key=self.coordinate_map_key,
                             coordinate_manager=self.coordinate_manager)
 
     def detach(self):
-        return SparseTensor(self._F.detach(), coordinate_map_key=self.coordinate_map_key,
+        return SparseTensor(self.F.detach(), coordinate_map_key=self.coordinate_map_key,
                             coordinate_manager=self.coordinate_manager)
 
 
@@ -414,8 +446,8 @@ class _Convolution(MinkowskiModuleBase):
                 self.bias.uniform_(-bound, bound)
 
     def forward(self, x: SparseTensor) -> SparseTensor:
-        if x.F.shape[1] != self.in_channels:
-            raise RuntimeError(f"Channel size mismatch {x.F.shape[1]} != {self.in_channels}")
+        if x.shape[1] != self.in_channels:
+            raise RuntimeError(f"Channel size mismatch {x.shape[1]} != {self.in_channels}")
         cm, in_key = x.coordinate_manager, x.coordinate_map_key
         if self.use_mm:
             # ME does F.mm here; tall inputs with 64-multiple channels take the tcgen05 GEMM (ops.LinearTC), the rest
@@ -431,7 +463,11 @@ class _Convolution(MinkowskiModuleBase):
         else:
             out_key = in_key
         kmap = cm.kernel_map(in_key, out_key, self.kernel_size, self.stride, self.dilation, self.is_transpose)
-        out = ops.SparseConv.apply(x.F.float(), self.kernel, self.bias, kmap, self._packs)
+        lazy = x._pending()
+        if lazy is not None and out_key == in_key and not self.is_transpose and lazy.dtype == torch.float32:
+            out = ops.bn_act_conv(lazy.bn, lazy.x, lazy.act, lazy.group, self.kernel, self.bias, kmap, self._packs)
+        else:
+            out = ops.SparseConv.apply(x.F.float(), self.kernel, self.bias, kmap, self._packs)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
     def extra_repr(self):
@@ -471,7 +507,10 @@ class MinkowskiBatchNorm(MinkowskiModuleBase):
     def forward(self, x):
         # training-mode statistics + apply run in the fused row kernels (ops.BatchNormAct; the convolution that produced
         # x already left its column sums); same parameters, buffers and running-statistics update as nn.BatchNorm1d
-        return _like(x, ops.batchnorm_rows(self.bn, x.F, ops.ACT_NONE, self._group()))
+        xf = x.F
+        if self.bn.training and self.bn.running_mean is not None and xf.is_cuda and xf.dtype == torch.float32:
+            return _like(x, _LazyRows(self.bn, xf, ops.ACT_NONE, self._group()))      # see _LazyRows
+        return _like(x, ops.batchnorm_rows(self.bn, xf, ops.ACT_NONE, self._group()))
 
 
 class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
@@ -516,8 +555,22 @@ def _pointwise(name: str, torch_cls):
     return _Op
 
 
-MinkowskiReLU = _pointwise("MinkowskiReLU", nn.ReLU)
-MinkowskiLeakyReLU = _pointwise("MinkowskiLeakyReLU", nn.LeakyReLU)
+def _activation(name: str, torch_cls, act_code: int):
+    base = _pointwise(name, torch_cls)
+
+    class _Act(base):
+        def forward(self, x):
+            lazy = x._pending()
+            if lazy is not None and lazy.act == ops.ACT_NONE and \
+                    (act_code != ops.ACT_LEAKY or abs(self.module.negative_slope - 0.01) < 1e-12):
+                return _like(x, lazy.with_act(act_code))          # folded into the pending BatchNorm apply
+            return base.forward(self, x)
+    _Act.__name__ = _Act.__qualname__ = name
+    return _Act
+
+
+MinkowskiReLU = _activation("MinkowskiReLU", nn.ReLU, ops.ACT_RELU)
+MinkowskiLeakyReLU = _activation("MinkowskiLeakyReLU", nn.LeakyReLU, ops.ACT_LEAKY)
 MinkowskiSigmoid = _pointwise("MinkowskiSigmoid", nn.Sigmoid)
 MinkowskiSoftmax = _pointwise("MinkowskiSoftmax", nn.Softmax)
 MinkowskiDropout = _pointwise("MinkowskiDropout", nn.Dropout)

@@ -614,6 +614,49 @@ def affine_act(x, scale, shift, act: int = 0, residual=None):
     return y
 
 
+def _bn_forward_coefs(x, gamma, beta, eps, group, running_mean, running_var, momentum):
+    """Training-mode BatchNorm coefficients of x [N, C]: column statistics (left by the producing convolution's epilogue
+    when available, else one reduction pass; summed over `group` for SyncBatchNorm) → one coefficient kernel that also
+    updates the running statistics.  Returns scale, shift (y = x*scale + shift), mean, rstd, count_dev."""
+    n, c = x.shape
+    dev = x.device
+    stats = take_pending_stats(x)
+    if stats is None:
+        stats = column_stats(x)
+    count_dev = None
+    if group is not None:
+        packed = torch.cat([stats.view(-1), torch.full((1,), float(n), dtype=torch.float64, device=dev)])
+        torch.distributed.all_reduce(packed, group=group)
+        stats, count_dev = packed[:-1].contiguous(), packed[-1:].contiguous()
+    scale, shift, mean, rstd = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
+    call("pasco_bn_finalize", ptr(stats), ptr(count_dev), C.c_double(float(n)), c, ptr(gamma), ptr(beta), C.c_float(eps),
+         C.c_float(momentum if momentum is not None else 0.1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+         ptr(running_mean), ptr(running_var))
+    return scale, shift, mean, rstd, count_dev
+
+
+def _bn_backward(gy, x, gamma, scale, shift, mean, rstd, count_dev, act, group, n):
+    """Gradient of y = act(BN(x)) w.r.t. x, gamma, beta: one reduce pass → one coefficient kernel → one apply pass."""
+    gy = gy.contiguous()
+    c = x.shape[1]
+    dev = x.device
+    sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
+    call("pasco_bn_bwd_reduce", ptr(gy), ptr(x), x.shape[0], c, ptr(scale), ptr(shift), act, ptr(sums))
+    div = 1.0
+    if group is not None:
+        # sums are global after the all-reduce; every rank then holds the global dgamma/dbeta, and the gradient
+        # all-reduce (mean over ranks) of the data-parallel step leaves them unchanged only if divided here
+        torch.distributed.all_reduce(sums, group=group)
+        div = float(torch.distributed.get_world_size(group))
+    ca, cb, cc, gg, gb = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(5))
+    call("pasco_bn_bwd_coefs", ptr(sums), ptr(count_dev), C.c_double(float(n)), c, ptr(gamma), ptr(mean), ptr(rstd),
+         C.c_float(div), ptr(ca), ptr(cb), ptr(cc), ptr(gg), ptr(gb))
+    gx = torch.empty_like(x)
+    call("pasco_bn_bwd_apply", ptr(gy), ptr(x), x.shape[0], c, ptr(scale), ptr(shift), act,
+         ptr(ca), ptr(cb), ptr(cc), ptr(gx))
+    return gx, gg, gb
+
+
 class BatchNormAct(torch.autograd.Function):
     """y = act(BN(x)) with training-mode batch statistics over all rows (optionally summed over ranks =
     SyncBatchNorm).  Forward: column sums → one coefficient kernel (scale/shift, mean/rstd, running statistics) →
@@ -622,46 +665,70 @@ class BatchNormAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, eps, act, group, running_mean=None, running_var=None, momentum=0.1):
         x = x.contiguous()
-        n, c = x.shape
-        dev = x.device
-        stats = take_pending_stats(x)
-        if stats is None:
-            stats = column_stats(x)
-        count_dev = None
-        if group is not None:
-            packed = torch.cat([stats.view(-1), torch.tensor([float(n)], dtype=torch.float64, device=dev)])
-            torch.distributed.all_reduce(packed, group=group)
-            stats, count_dev = packed[:-1].contiguous(), packed[-1:].contiguous()
-        scale, shift, mean, rstd = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
-        call("pasco_bn_finalize", ptr(stats), ptr(count_dev), C.c_double(float(n)), c, ptr(gamma), ptr(beta), C.c_float(eps),
-             C.c_float(momentum if momentum is not None else 0.1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
-             ptr(running_mean), ptr(running_var))
+        scale, shift, mean, rstd, count_dev = _bn_forward_coefs(x, gamma, beta, eps, group, running_mean, running_var, momentum)
         y = affine_act(x, scale, shift, act)
         ctx.save_for_backward(x, gamma, scale, shift, mean, rstd, count_dev)
-        ctx.act, ctx.group, ctx.n = act, group, n
+        ctx.act, ctx.group, ctx.n = act, group, x.shape[0]
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, gamma, scale, shift, mean, rstd, count_dev = ctx.saved_tensors
-        gy = gy.contiguous()
-        c = x.shape[1]
-        dev = x.device
-        sums = torch.zeros(2, c, dtype=torch.float64, device=dev)
-        call("pasco_bn_bwd_reduce", ptr(gy), ptr(x), x.shape[0], c, ptr(scale), ptr(shift), ctx.act, ptr(sums))
-        div = 1.0
-        if ctx.group is not None:
-            # sums are global after the all-reduce; every rank then holds the global dgamma/dbeta, and the gradient
-            # all-reduce (mean over ranks) of the data-parallel step leaves them unchanged only if divided here
-            torch.distributed.all_reduce(sums, group=ctx.group)
-            div = float(torch.distributed.get_world_size(ctx.group))
-        ca, cb, cc, gg, gb = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(5))
-        call("pasco_bn_bwd_coefs", ptr(sums), ptr(count_dev), C.c_double(float(ctx.n)), c, ptr(gamma), ptr(mean), ptr(rstd),
-             C.c_float(div), ptr(ca), ptr(cb), ptr(cc), ptr(gg), ptr(gb))
-        gx = torch.empty_like(x)
-        call("pasco_bn_bwd_apply", ptr(gy), ptr(x), x.shape[0], c, ptr(scale), ptr(shift), ctx.act,
-             ptr(ca), ptr(cb), ptr(cc), ptr(gx))
+        gx, gg, gb = _bn_backward(gy, x, gamma, scale, shift, mean, rstd, count_dev, ctx.act, ctx.group, ctx.n)
         return gx, gg, gb, None, None, None, None, None, None
+
+
+class BNActConv(torch.autograd.Function):
+    """out = SparseConv(act(BN(x)))  as ONE autograd node on the plane-gather path: the BatchNorm apply pass writes the
+    normalised activations directly as bf16 planes (hi [+ lo]) — the only form the convolution and its weight gradient
+    read — so the fp32 copy of act(BN(x)) never exists: same HBM bytes as the plain apply pass, no separate split pass,
+    and the planes double as the saved tensor of the backward pass (pre-activation residual blocks, mink.py:618-658:
+    BN → ReLU → conv, twice per block)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, weight, bias, eps, act, group, running_mean, running_var, momentum, kmap, packs):
+        x = x.contiguous()
+        scale, shift, mean, rstd, count_dev = _bn_forward_coefs(x, gamma, beta, eps, group, running_mean, running_var, momentum)
+        hi, lo = split_planes(x, scale, shift, act)
+        out = conv_apply(x, weight, kmap.nbr, kmap.n_out, False, None, bias.view(-1).contiguous() if bias is not None else None,
+                         packs=packs, want_stats=True, planes=(hi, lo))
+        ctx.kmap, ctx.packs, ctx.has_bias = kmap, packs, bias is not None
+        ctx.act, ctx.group, ctx.n, ctx.has_lo = act, group, x.shape[0], lo is not None
+        ctx.save_for_backward(x, gamma, scale, shift, mean, rstd, count_dev, weight, hi, *([lo] if lo is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, scale, shift, mean, rstd, count_dev, weight, hi = ctx.saved_tensors[:9]
+        lo = ctx.saved_tensors[9] if ctx.has_lo else None
+        kmap = ctx.kmap
+        g = g.contiguous()
+        K, Cin, Cout = weight.shape
+        g_planes = split_planes(g)
+        nbr_t, koff_t = kmap.transposed()
+        gy = conv_apply(g, weight, nbr_t, kmap.n_in, True, koff_t, packs=ctx.packs, planes=g_planes)
+        gw = conv_wgrad(x, g, kmap.nbr, K, Cin, Cout, in_planes=(hi, lo), g_planes=g_planes) if ctx.needs_input_grad[3] else None
+        gb = g.sum(0, keepdim=True) if ctx.has_bias and ctx.needs_input_grad[4] else None
+        gx, gg, gbeta = _bn_backward(gy, x, gamma, scale, shift, mean, rstd, count_dev, ctx.act, ctx.group, ctx.n)
+        return gx, gg, gbeta, gw, gb, None, None, None, None, None, None, None, None
+
+
+def bn_act_conv(bn, x: torch.Tensor, act: int, group, weight, bias, kmap: "KernelMap", packs=None) -> torch.Tensor:
+    """conv(act(BatchNorm(x))) — fused (BNActConv) when the layer runs on the plane-gather tensor-core path in training
+    mode, the two separate nodes otherwise."""
+    K, Cin, Cout = weight.shape
+    fused = (bn.training and bn.running_mean is not None and x.is_cuda and _planes_ok(Cin, kmap.K, kmap.nbr)
+             and _tc_ok(Cin, Cout, kmap.K, "fwd") and _tc_ok(Cout, Cin, kmap.K, "dgrad") and _tc_ok(Cin, 64, 1, "wgrad")
+             and Cout % 64 == 0 and Cout <= 256
+             and not (_SPLIT_K and load().pasco_conv_splitk_workspace_bytes(kmap.K, kmap.n_out, Cout) > 0)
+             and not (_SPLIT_K and load().pasco_conv_splitk_workspace_bytes(kmap.K, kmap.n_in, Cin) > 0))
+    if not fused:
+        return SparseConv.apply(batchnorm_rows(bn, x, act, group), weight, bias, kmap, packs)
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    return BNActConv.apply(x, bn.weight, bn.bias, weight, bias, bn.eps, act, group, bn.running_mean, bn.running_var, mom,
+                           kmap, packs)
 
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2

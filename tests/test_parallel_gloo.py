@@ -31,6 +31,21 @@ def _worker(rank, world, port, out):
         ok &= torch.allclose(p.grad, sum(parts) / world, atol=1e-7)
     bucket2 = parallel.allreduce_gradients(params, bucket=bucket)
     ok &= bucket2 is bucket
+    # bucketed reducer overlapped with backward: gradients are views into one flat buffer, unused parameters reduce as zeros
+    model2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    model2.load_state_dict(model.state_dict())
+    params2 = list(model2.parameters())
+    red = parallel.GradReducer(params2, bucket_mb=16 * 4 / (1 << 20))          # 16-float buckets → several buckets
+    ok &= len(red.buckets) >= 3
+    for _ in range(2):                                                          # two steps: zero_grad re-arms the hooks
+        red.zero_grad()
+        model2[:3](x).square().mean().backward()
+        red.finish()
+        for i, p in enumerate(params2):
+            parts = [g[i] if g[i] is not None else torch.zeros_like(p) for g in gathered]
+            ok &= torch.allclose(p.grad, sum(parts) / world, atol=1e-7)
+            ok &= p.grad.data_ptr() >= red.flat.data_ptr() and p.grad.data_ptr() < red.flat.data_ptr() + red.flat.numel() * 4
+    red.detach()
     # packed SyncBN statistics
     xs = torch.randn(10 + 3 * rank, 6, dtype=torch.float64, generator=torch.Generator().manual_seed(7 + rank))
     stats = torch.stack([xs.sum(0), (xs * xs).sum(0)])
