@@ -46,6 +46,12 @@ def _worker(rank, world, port, out):
             ok &= torch.allclose(p.grad, sum(parts) / world, atol=1e-7)
             ok &= p.grad.data_ptr() >= red.flat.data_ptr() and p.grad.data_ptr() < red.flat.data_ptr() + red.flat.numel() * 4
     red.detach()
+    # variable-length row all-gather (the sparse logit exchange of MIMO head sharding)
+    rows = torch.arange((3 + 2 * rank) * 4, dtype=torch.float32).view(3 + 2 * rank, 4) + 100 * rank
+    got = parallel.all_gather_rows(rows)
+    ok &= len(got) == world and all(g.shape[0] == 3 + 2 * r for r, g in enumerate(got))
+    ok &= all(torch.equal(g, torch.arange((3 + 2 * r) * 4, dtype=torch.float32).view(3 + 2 * r, 4) + 100 * r) for r, g in enumerate(got))
+    ok &= parallel.all_gather_rows(torch.zeros(0 if rank == 0 else 2, 3))[0].shape == (0, 3)
     # packed SyncBN statistics
     xs = torch.randn(10 + 3 * rank, 6, dtype=torch.float64, generator=torch.Generator().manual_seed(7 + rank))
     stats = torch.stack([xs.sum(0), (xs * xs).sum(0)])
