@@ -61,15 +61,27 @@ def _peaks():
     return 6650.0, 1400.0, "fallback"
 
 
+NCU_FILE = "r02_ncu_conv_planes.json"
+
+
+def _kernel_name(kind, meta):
+    path = meta.get("path", "regs")
+    if path == "planes":
+        return "k_wgrad_pl" if kind == "wgrad" else "k_conv_pl"
+    if path == "simt":
+        return "k_wgrad_simt" if kind == "wgrad" else "k_conv_simt"
+    return "k_wgrad_tc" if kind == "wgrad" else "k_conv_tc"
+
+
 def _ncu_traffic(kind, meta):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes) per launch of the dominant kernel from the committed
-    ncu --set full capture of the same layer shape (profiles/r01_ncu_conv_v4.json: N=1.05 M rows, C=64, bf16x3);
+    ncu --set full capture of the same layer shape (profiles/r02_ncu_conv_planes.json: N=1.05 M rows, C=64, bf16x3);
     None if the dominant group is another shape or the capture is absent."""
     if not (meta["Cin"] == 64 and meta["Cout"] == 64 and meta["K"] == 27 and 0.9e6 < meta["n_out"] < 1.2e6 and meta["precision"] == 3):
         return None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_conv_v4.json")))
-        want = "k_wgrad_tc" if kind == "wgrad" else "k_conv_tc"
+        d = json.load(open(os.path.join(ROOT, "profiles", NCU_FILE)))
+        want = _kernel_name(kind, meta)
         for k in d["kernels"]:
             if want in k["kernel"]:
                 tot = 0.0
@@ -330,7 +342,7 @@ def run_ours(a):
     # ---- roofline of the dominant kernel (per-launch CUDA-event durations recorded inside the timed region) ----
     groups = {}
     for kind, e_a, e_b, m in prof:
-        key = (kind, m["n_out"] // 50000, m["K"], m["Cin"], m["Cout"])
+        key = (kind, m["n_out"] // 50000, m["K"], m["Cin"], m["Cout"], m.get("path"))
         g = groups.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0, "kind": kind, "meta": m})
         pairs = float(m["pairs"].item()) if m.get("pairs") is not None else float(m["n_out"]) * (m["K"] if m["K"] > 1 else 1)
         g["ms"] += e_a.elapsed_time(e_b)
@@ -350,10 +362,10 @@ def run_ours(a):
         ach_tf = top["flops"] / top["n"] / per_launch_ms / 1e9
         ach_gb = top["bytes"] / top["n"] / per_launch_ms / 1e6
         m = top["meta"]
-        roof = {"kernel": f"k_conv_tc<{m['precision']}> {top['kind']} K={m['K']} {m['Cin']}->{m['Cout']} n_out~{m['n_out']}",
+        roof = {"kernel": f"{_kernel_name(top['kind'], m)}<{m['precision']}> {top['kind']} K={m['K']} {m['Cin']}->{m['Cout']} n_out~{m['n_out']}",
                 "bound": "tensor", "achieved": round(ach_tf, 2), "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": round(ach_tf / tf_peak, 4), "traffic": _ncu_traffic(top["kind"], m),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_conv_v4.json (same layer shape)",
+                "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/{NCU_FILE} (same layer shape)",
                 "algorithmic_bytes_per_launch": round(top["bytes"] / top["n"]), "peak_source": peak_src,
                 "launch_ms": round(per_launch_ms, 4), "launches": top["n"],
                 "algorithmic": "flops = 2*pairs*Cin*Cout per launch (useful MACs; bf16x3 issues 3x that on the tensor pipe)",

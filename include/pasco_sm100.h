@@ -40,9 +40,11 @@ int pasco_device_info(int* sm_count, int* smem_optin, int* cc);
 
 /* ME.SparseTensor(F, C) — pasco/models/net_panoptic_sparse.py:323, unet3d_sparse_v2.py:207.
  * Inserts n rows; on return table_vals[slot(key)] = smallest row index holding that key and
- * first_row[i] = that winning row for input row i (first_row[i]==i ⇔ row i is kept).        */
+ * first_row[i] = that winning row for input row i (first_row[i]==i ⇔ row i is kept).
+ * Keys pack 16 bits per component: a coordinate or batch index outside [-32768, 32767] sets *err_flag = 2 on the
+ * device (err_flag may be NULL) and the host wrapper raises; MinkowskiEngine accepts the full int32 range.          */
 int pasco_hash_insert(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals,
-                      int64_t capacity, int32_t* first_row, pasco_stream_t s);
+                      int64_t capacity, int32_t* first_row, int32_t* err_flag, pasco_stream_t s);
 
 /* After compaction: rewrite table values old_row → new_row[old_row] (new_row[i] = −1 for dropped rows). */
 int pasco_hash_remap(int32_t* table_vals, int64_t capacity, const int32_t* new_row, pasco_stream_t s);
@@ -153,12 +155,6 @@ int pasco_conv_forward_splitk(const float* in, int64_t n_in, const int32_t* nbr,
                               const float* in_scale, const float* in_shift, int32_t in_act, float* out, int32_t precision,
                               int64_t in_pitch, int64_t out_pitch, void* workspace, int64_t workspace_bytes,
                               pasco_stream_t s);
-
-/* Two kernels implement pasco_conv_forward_tc: the register-gather kernel (variant 0, default) and a TMA-gather kernel
- * (variant 1: tile::gather4 fetches the neighbour rows into a raw shared-memory ring, warps only convert; used when
- * Cout <= 128 leaves room for that ring, otherwise variant 0 runs).  Results are identical bit for bit (same operand
- * split, same MMA order); measured speeds are in DESIGN.md section 3.4.                                             */
-int pasco_conv_set_variant(int32_t variant);
 
 /* Plane-gather path (the default for every gathered convolution): the activations are split ONCE per tensor into bf16
  * planes x = hi + lo (lo = NULL for precision 1) by pasco_split_planes — optionally fused with y = act(x*scale + shift),

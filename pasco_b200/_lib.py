@@ -22,7 +22,7 @@ PROTOTYPES = {
     "pasco_last_error": (C.c_char_p, []),
     "pasco_abi_version": (C.c_int, []),
     "pasco_device_info": (C.c_int, [_p, _p, _p]),
-    "pasco_hash_insert": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "pasco_hash_insert": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p, _p]),
     "pasco_hash_remap": (C.c_int, [_p, _i64, _p, _p]),
     "pasco_hash_lookup": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
     "pasco_coords_floor": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
@@ -43,7 +43,6 @@ PROTOTYPES = {
     "pasco_conv_forward_tc": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _i32, _i64, _i64, _p]),
     "pasco_conv_splitk_workspace_bytes": (_i64, [_i32, _i64, _i32]),
     "pasco_conv_forward_splitk": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i32, _i64, _i64, _p, _i64, _p]),
-    "pasco_conv_set_variant": (C.c_int, [_i32]),
     "pasco_split_planes": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i32, _p, _p, _p]),
     "pasco_conv_forward_planes": (C.c_int, [_p, _p, _i64, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i32, _i64, _i64, _p]),
     "pasco_conv_wgrad_planes": (C.c_int, [_p, _p, _i64, _p, _i32, _i64, _i32, _i32, _p, _p, _p, _i32, _i64, _i64, _p]),

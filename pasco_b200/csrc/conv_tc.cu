@@ -22,7 +22,6 @@
 // hi·hi + lo·hi + hi·lo accumulate in fp32 — ~2^-16 relative error, well inside the 1e-3 parity bound.
 #include "common.cuh"
 #include "umma.cuh"
-#include "tma.cuh"
 #include <cstdlib>
 
 using namespace pasco;
@@ -137,7 +136,7 @@ struct SlotIt {
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// consumer-side roles shared by the register-gather kernel (k_conv_tc) and the TMA-gather kernel (k_conv_tma)
+// consumer-side roles shared by the register-gather kernel (k_conv_tc) and the plane-gather kernel (k_conv_pl)
 // ------------------------------------------------------------------------------------------------------------
 struct Pipe {
   uint8_t* a_smem;          // [sa][A_hi | A_lo]
@@ -555,284 +554,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// TMA-gather variant of the same convolution (Cout <= 128)
-// ------------------------------------------------------------------------------------------------------------
-// The register gather above is latency bound: ncu shows 3.5 long-scoreboard stall cycles per issued instruction and the
-// L2 at 15 % of its bandwidth, i.e. ~28 KB of row segments in flight per SM is all the 8 gather warps' registers can
-// hold.  Here the TMA engine does the gather: `tile::gather4` fetches 4 arbitrary fp32 rows x 64 channels (256 B each)
-// per instruction straight from the feature tensor into a raw shared-memory ring (no registers, R x 32 KB in flight),
-// and the former gather warps only CONVERT: ld.shared fp32 → optional BatchNorm affine + activation → bf16 hi/lo
-// split → st.shared into the 128-byte-swizzled UMMA tile.
-//   warps 0-7   convert   (16 tile rows each; 8 lanes x 2 ld.shared.v4 per row)
-//   warps 8-11  epilogue, warp 12 MMA issuer, warp 13 weight loader      (shared with k_conv_tc)
-//   warps 14-17 TMA issue: warp w owns raw slot w and the stages n ≡ w (mod R); lane l fetches tile rows 4l..4l+3.
-// Missing neighbours (-1) must not reach the TMA — its out-of-range zero fill is 4.5x slower than a fetch, and one
-// shared dummy row hot-spots an L2 slice — so the issuing lane substitutes its own output row index (valid, distinct
-// per lane, L2-friendly) and flags the row in a byte mask; the convert warps write zeros for flagged rows.
-constexpr int CV_WARPS = 8;                               // convert warps 0-7
-constexpr int T_MMA_WARP = CV_WARPS + NUM_EPI_WARPS;      // 12 (epilogue = warps 8-11)
-constexpr int T_LOAD_WARP = T_MMA_WARP + 1;               // 13
-constexpr int TMA_WARP0 = T_LOAD_WARP + 1;                // 14
-constexpr int MAX_TMA_WARPS = 8;
-constexpr int MAX_RAW_SLOTS = 16;
-constexpr int IDX_DEPTH = 2;                              // neighbour-index ring entries per issue warp (all smem allows)
-constexpr int NUM_THREADS_TMA = (TMA_WARP0 + MAX_TMA_WARPS) * 32;   // 704
-
-// The raw ring is cut into SUB = 32-row sub-stages (32 rows x 64 fp32 = 8 KB, 4 per A tile).  Sub-stage m belongs to
-// issue warp m % 8 AND to convert warp m % 8: the pair works as a private producer / consumer while the other 7 pairs
-// work on other sub-stages — one warp's gather4s are serialised (~63 ns each, measured), and a convert warp's chain
-// (wait → ld.shared → split → st.shared → fence → arrive) is latency bound, so 8 independent chains are what keeps the
-// SM's TMA path busy (it saturates at ~11 ns per 1-KB gather4).
-template <int NSPLIT, bool PROLOGUE>
-__global__ void __launch_bounds__(NUM_THREADS_TMA, 1) k_conv_tma(const __grid_constant__ ConvParams p,
-                                                                 const __grid_constant__ CUtensorMap tm_in, int S, int NW, int sub_rows,
-                                                                 int n_in) {
-  // No alignment slack here (every byte of the 227 KB is spoken for): the dynamic shared window starts 1024-byte
-  // aligned when the kernel has no static shared memory, which the SWIZZLE_128B tiles need; checked below.
-  extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int n_op = (NSPLIT == 3) ? 2 : 1;
-  const int b_tile = p.Cout * 128;
-  const int a_stage_bytes = n_op * A_TILE_BYTES;
-  const int b_stage_bytes = n_op * b_tile;
-  const int T = p.tiles_per_group;
-  const int sub_bytes = sub_rows * KBLK * 4;                                 // raw bytes of one sub-stage
-  const int H = BLOCK_M / sub_rows;                                          // sub-stages per A tile
-  uint8_t* raw_smem = smem;                                                  // [S][sub_rows][64 fp32]
-  uint8_t* a_smem = raw_smem + (size_t)S * sub_bytes;                        // [sa][A_hi | A_lo]
-  uint8_t* b_smem = a_smem + (size_t)p.sa * a_stage_bytes;                   // [sb][B_hi | B_lo]
-  uint8_t* rawmask = b_smem + (size_t)p.sb * b_stage_bytes;                  // [S][32] 1 = missing neighbour
-  int* idx_ring = reinterpret_cast<int*>(rawmask + MAX_RAW_SLOTS * 32);      // [MAX_TMA_WARPS][IDX_DEPTH][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_ring + MAX_TMA_WARPS * IDX_DEPTH * 32);
-  uint64_t* afull = bars;                         // [2]
-  uint64_t* aempty = bars + 2;                    // [2]
-  uint64_t* bfull = bars + 4;                     // [2]
-  uint64_t* bempty = bars + 6;                    // [2]
-  uint64_t* tfull = bars + 8;                     // [2]
-  uint64_t* tempty = bars + 10;                   // [2]
-  uint64_t* rfull = bars + 12;                    // [MAX_RAW_SLOTS]
-  uint64_t* rempty = rfull + MAX_RAW_SLOTS;       // [MAX_RAW_SLOTS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + MAX_RAW_SLOTS);
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.Cin / KBLK;
-  const int64_t num_tiles = (p.n_out + BLOCK_M - 1) / BLOCK_M;
-  const int64_t num_groups = (num_tiles + T - 1) / T;
-  const int acc_cols = T * p.Cout;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(afull + s), H);                  // one arrival per converted sub-stage
-      mbar_init(smem_u32(aempty + s), 1);
-      mbar_init(smem_u32(bfull + s), 1);
-      mbar_init(smem_u32(bempty + s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(tfull + b), 1);
-      mbar_init(smem_u32(tempty + b), NUM_EPI_WARPS);
-    }
-    for (int r = 0; r < MAX_RAW_SLOTS; ++r) {
-      mbar_init(smem_u32(rfull + r), 1);                  // one arrive.expect_tx by the issuing warp + the slot's bytes
-      mbar_init(smem_u32(rempty + r), 1);                 // the slot's convert warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == T_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  Pipe pl;
-  pl.a_smem = a_smem; pl.b_smem = b_smem;
-  pl.afull = afull; pl.aempty = aempty; pl.bfull = bfull; pl.bempty = bempty; pl.tfull = tfull; pl.tempty = tempty;
-  pl.tmem_base = tmem_base;
-  pl.stat_acc = nullptr;
-  pl.a_stage_bytes = a_stage_bytes; pl.b_stage_bytes = b_stage_bytes; pl.b_tile = b_tile;
-  pl.KB = KB; pl.T = T; pl.acc_cols = acc_cols; pl.num_tiles = num_tiles; pl.num_groups = num_groups;
-
-  if (warp >= TMA_WARP0 || warp < CV_WARPS) {
-    // ============================ TMA issue (warps 14-21) and convert (warps 0-7) pairs ============================
-    // Pair tw owns the sub-stages m = tw + NW*i.  NW is a multiple of H, so the pair always works on quarter
-    // h = tw % H of the A stages n = tw / H + (NW / H) * i: the cursor below walks A stages.
-    const bool is_issue = warp >= TMA_WARP0;
-    const int tw = is_issue ? warp - TMA_WARP0 : warp;
-    const int h = tw % H;
-    const int sstep = NW / H;                                // A stages per step of this pair
-    struct Cur {
-      int64_t group, n;
-      int k, kb, t, teff;
-      bool valid;
-    };
-    auto advance = [&](Cur& c, int steps) {
-      for (int s_ = 0; s_ < steps && c.valid; ++s_) {
-        ++c.n;
-        if (++c.t < c.teff) continue;
-        c.t = 0;
-        if (++c.kb < KB) continue;
-        c.kb = 0;
-        if (++c.k < p.K) continue;
-        c.k = 0;
-        c.group += gridDim.x;
-        c.valid = c.group < num_groups;
-        if (c.valid) {
-          const int64_t rem = num_tiles - c.group * T;
-          c.teff = rem < T ? (int)rem : T;
-        }
-      }
-    };
-    Cur cur;
-    cur.group = blockIdx.x; cur.n = 0; cur.k = 0; cur.kb = 0; cur.t = 0;
-    {
-      const int64_t rem0 = num_tiles - cur.group * T;
-      cur.teff = rem0 < T ? (int)rem0 : T;
-    }
-    cur.valid = cur.group < num_groups && tw < NW;
-    advance(cur, tw / H);
-    int slot = tw;                                   // tw < NW <= S
-    uint32_t phase = 0;
-    auto next_slot = [&]() {
-      slot += NW;
-      if (slot >= S) {
-        slot -= S;
-        phase ^= 1u;
-      }
-    };
-    if (is_issue) {
-      // neighbour indices travel through a private cp.async ring IDX_DEPTH-1 steps ahead of the issue (the table is
-      // streamed from HBM: a register prefetch one step ahead left the warp stalled on the load most of the time)
-      int* ring = idx_ring + tw * (IDX_DEPTH * 32);
-      const bool issuing = lane * 4 < sub_rows;      // sub_rows / 4 lanes issue one gather4 each
-      auto prefetch = [&](const Cur& c, int e) {
-        int* d = ring + (e % IDX_DEPTH) * 32 + lane;
-        if (c.valid && lane < sub_rows) {
-          const int64_t row = (c.group * T + c.t) * BLOCK_M + h * sub_rows + lane;
-          if (row < p.n_out) {
-            if (p.nbr) cp_async4(smem_u32(d), p.nbr + (int64_t)c.k * p.n_out + row);
-            else *d = (int)row;
-          } else {
-            *d = -1;
-          }
-        }
-        cp_async_commit();
-      };
-      Cur pf = cur;
-      int pf_e = 0, cur_e = 0;
-      for (int d = 0; d < IDX_DEPTH - 1; ++d) {
-        prefetch(pf, pf_e++);
-        advance(pf, sstep);
-      }
-      while (cur.valid) {
-        prefetch(pf, pf_e++);
-        advance(pf, sstep);
-        cp_async_wait<IDX_DEPTH - 1>();              // the entry of `cur` has landed (groups complete in order)
-        __syncwarp();
-        int4 v = make_int4(0, 0, 0, 0);
-        uint32_t miss = 0;
-        if (issuing) {
-          v = *reinterpret_cast<const int4*>(ring + (cur_e % IDX_DEPTH) * 32 + 4 * lane);
-          const int64_t row = (cur.group * T + cur.t) * BLOCK_M + h * sub_rows + 4 * lane;
-          // a missing neighbour fetches some valid row instead (its own output row: distinct per lane, L2 friendly)
-          // and is zeroed by the convert warp
-          const uint32_t sub = (uint32_t)row % (uint32_t)n_in;       // rows < 2^31 (int32 neighbour tables)
-          if (v.x < 0) { miss |= 0x1u; v.x = (int)sub; }
-          if (v.y < 0) { miss |= 0x100u; v.y = (int)(sub + 1 < (uint32_t)n_in ? sub + 1 : sub); }
-          if (v.z < 0) { miss |= 0x10000u; v.z = (int)(sub + 2 < (uint32_t)n_in ? sub + 2 : sub); }
-          if (v.w < 0) { miss |= 0x1000000u; v.w = (int)(sub + 3 < (uint32_t)n_in ? sub + 3 : sub); }
-        }
-        ++cur_e;
-        const int col = cur.kb * KBLK;
-        const uint32_t fbar = smem_u32(rfull + slot), ebar = smem_u32(rempty + slot);
-        mbar_wait(ebar, phase ^ 1u);
-        if (issuing) reinterpret_cast<uint32_t*>(rawmask + slot * 32)[lane] = miss;
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(fbar, (uint32_t)sub_bytes);
-        __syncwarp();
-        if (issuing)
-          tma::gather4(smem_u32(raw_smem + (size_t)slot * sub_bytes) + (uint32_t)lane * 1024u, &tm_in, col, v.x, v.y, v.z, v.w, fbar);
-        advance(cur, sstep);
-        next_slot();
-      }
-      cp_async_wait<0>();
-    } else {
-      // convert: raw fp32 rows → optional BatchNorm affine + activation → bf16 hi/lo → swizzled UMMA tile
-      const int j8 = lane & 7;          // this lane's two 16-byte fp32 chunks: channels 4*j8.. and 32 + 4*j8..
-      const int rsub = lane >> 3;       // 4 rows per instruction
-      const bool affine = PROLOGUE && p.in_scale != nullptr;
-      while (cur.valid) {
-        float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sc1 = sc0, sh1 = sh0;
-        if (PROLOGUE && affine) {
-          const int c0 = cur.kb * KBLK + 4 * j8;
-          sc0 = __ldg(reinterpret_cast<const float4*>(p.in_scale + c0));
-          sh0 = __ldg(reinterpret_cast<const float4*>(p.in_shift + c0));
-          sc1 = __ldg(reinterpret_cast<const float4*>(p.in_scale + c0 + 32));
-          sh1 = __ldg(reinterpret_cast<const float4*>(p.in_shift + c0 + 32));
-        }
-        const int aslot = (int)(cur.n % p.sa);
-        const uint32_t aph = (uint32_t)((cur.n / p.sa) & 1);
-        mbar_wait(smem_u32(rfull + slot), phase);
-        mbar_wait(smem_u32(aempty + aslot), aph ^ 1u);
-        const uint8_t* raw = raw_smem + (size_t)slot * sub_bytes;
-        const uint8_t* msk = rawmask + slot * 32;
-        uint8_t* dst = a_smem + (size_t)aslot * a_stage_bytes;
-        for (int i = 0; i < sub_rows; i += 4) {
-          const uint32_t srow = (uint32_t)(i + rsub);                             // row inside the sub-stage
-          const uint32_t trow = (uint32_t)(h * sub_rows) + srow;                  // row inside the A tile
-          float4 x0 = *reinterpret_cast<const float4*>(raw + srow * 256u + j8 * 16u);
-          float4 x1 = *reinterpret_cast<const float4*>(raw + srow * 256u + 128u + j8 * 16u);
-          const bool missing = msk[srow] != 0;
-          if (PROLOGUE) {
-            x0.x = act_apply(fmaf(x0.x, sc0.x, sh0.x), p.in_act); x0.y = act_apply(fmaf(x0.y, sc0.y, sh0.y), p.in_act);
-            x0.z = act_apply(fmaf(x0.z, sc0.z, sh0.z), p.in_act); x0.w = act_apply(fmaf(x0.w, sc0.w, sh0.w), p.in_act);
-            x1.x = act_apply(fmaf(x1.x, sc1.x, sh1.x), p.in_act); x1.y = act_apply(fmaf(x1.y, sc1.y, sh1.y), p.in_act);
-            x1.z = act_apply(fmaf(x1.z, sc1.z, sh1.z), p.in_act); x1.w = act_apply(fmaf(x1.w, sc1.w, sh1.w), p.in_act);
-          }
-          if (missing) {
-            x0 = make_float4(0.f, 0.f, 0.f, 0.f);
-            x1 = x0;
-          }
-          // bf16 byte offset of channel 4*j8 in the 128-byte row = 8*j8 → chunk j8>>1, half j8&1; +32 ch = +4 chunks
-          const uint32_t sw = trow & 7u;
-          const uint32_t off0 = trow * 128u + ((((uint32_t)j8 >> 1) ^ sw) << 4) + (((uint32_t)j8 & 1u) << 3);
-          const uint32_t off1 = trow * 128u + (((4u + ((uint32_t)j8 >> 1)) ^ sw) << 4) + (((uint32_t)j8 & 1u) << 3);
-          if (NSPLIT == 3) {
-            uint2 h0, l0, h1, l1;
-            split4(x0, h0, l0);
-            split4(x1, h1, l1);
-            *reinterpret_cast<uint2*>(dst + off0) = h0;
-            *reinterpret_cast<uint2*>(dst + off1) = h1;
-            *reinterpret_cast<uint2*>(dst + A_TILE_BYTES + off0) = l0;
-            *reinterpret_cast<uint2*>(dst + A_TILE_BYTES + off1) = l1;
-          } else {
-            *reinterpret_cast<uint2*>(dst + off0) = to_bf16x4(x0);
-            *reinterpret_cast<uint2*>(dst + off1) = to_bf16x4(x1);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(afull + aslot));
-          mbar_arrive(smem_u32(rempty + slot));
-        }
-        advance(cur, sstep);
-        next_slot();
-      }
-    }
-  } else if (warp == T_LOAD_WARP) {
-    if (lane == 0) role_weight_loader(p, pl);
-  } else if (warp == T_MMA_WARP) {
-    if (lane == 0) role_mma<NSPLIT>(p, pl);
-  } else {
-    role_epilogue(p, pl, warp - CV_WARPS, lane);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == T_MMA_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // Plane-gather variant: the input arrives PRE-SPLIT as bf16 planes (hi [+ lo]) and the producers only move bytes
 // ------------------------------------------------------------------------------------------------------------
 // ncu of k_conv_tc (round 1): 3.5 long-scoreboard stall cycles per issued instruction, L2 at 15 % — every gathered
@@ -1016,13 +737,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
   }
 }
 
-// 0 = register-gather kernel everywhere (default: it is the faster one in fp32 mode),
-// 1 = TMA-gather kernel where eligible; PASCO_CONV_TMA overrides at load
-int& conv_variant() {
-  static int v = [] { const char* e = getenv("PASCO_CONV_TMA"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
 int pow2_cols(int c) {
   int v = 32;
   while (v < c) v <<= 1;
@@ -1030,12 +744,6 @@ int pow2_cols(int c) {
 }
 
 }  // namespace
-
-extern "C" int pasco_conv_set_variant(int32_t variant) {
-  PASCO_CHECK_ARG(variant == 0 || variant == 1, "pasco_conv_set_variant: variant must be 0 (register gather) or 1 (TMA gather)");
-  conv_variant() = variant;
-  return 0;
-}
 
 extern "C" int64_t pasco_conv_packed_bytes(int32_t K, int32_t Cin, int32_t Cout) {
   return (int64_t)K * Cin * Cout * 4;
@@ -1144,39 +852,6 @@ int conv_forward_impl(const float* in, int64_t n_in, const int32_t* nbr, int32_t
   int grid = (int)(groups < num_sms() ? groups : num_sms());
   cudaError_t e;
   const bool prologue = in_scale != nullptr || in_act != 0;
-  // ---- TMA-gather variant (k_conv_tma): Cout <= 128 leaves room for a raw fp32 ring next to the operand rings ----
-  if (conv_variant() && stats == nullptr && ksplit <= 1 && n_in >= 1 && ((p.in_pitch * 4) % 16) == 0) {
-    const int sa_t = 2, sb_t = 2;
-    const int sub_rows = 32;      // 4 sub-stages per A tile: a convert warp then advances 2 A stages per step <= sa (phase rule)
-    const int sub_bytes = sub_rows * KBLK * 4;
-    const int fixed_t = MAX_RAW_SLOTS * 32 + MAX_TMA_WARPS * IDX_DEPTH * 32 * 4 + (12 + 2 * MAX_RAW_SLOTS) * 8 + 16;
-    int S = (smem_optin - fixed_t - sa_t * a_stage - sb_t * b_stage) / sub_bytes;
-    // issue / convert pairs own private raw slots: S must be a multiple of the pair count NW (a multiple of 4)
-    int NW = 0;
-    if (S >= 16) { S = 16; NW = 8; }          // two slots per pair: the next fetch overlaps landing + conversion
-    else if (S >= 12) { S = 12; NW = 4; }     // three slots for each of 4 pairs
-    else if (S >= 8) { S = 8; NW = 8; }
-    CUtensorMap tm_in;
-    if (NW && tma::make_row_gather_map(&tm_in, in, n_in, Cin, p.in_pitch * 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, KBLK,
-                                       CU_TENSOR_MAP_SWIZZLE_NONE)) {
-      ConvParams q = p;
-      q.sa = sa_t; q.sb = sb_t;
-      const size_t smem_t = (size_t)S * sub_bytes + (size_t)sa_t * a_stage + (size_t)sb_t * b_stage + fixed_t;
-      auto launch_t = [&](auto kern) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
-        if (err == cudaSuccess) kern<<<grid, NUM_THREADS_TMA, smem_t, (cudaStream_t)s>>>(q, tm_in, S, NW, sub_rows, (int)n_in);
-        return err;
-      };
-      if (precision == 3) e = prologue ? launch_t(k_conv_tma<3, true>) : launch_t(k_conv_tma<3, false>);
-      else e = prologue ? launch_t(k_conv_tma<1, true>) : launch_t(k_conv_tma<1, false>);
-      if (e != cudaSuccess) {
-        set_error("pasco_conv_forward_tc: cudaFuncSetAttribute(%zu bytes) failed: %s", smem_t, cudaGetErrorString(e));
-        return -1;
-      }
-      PASCO_CHECK_LAUNCH("pasco_conv_forward_tc(tma)");
-      return 0;
-    }
-  }
   auto launch = [&](auto kern) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err == cudaSuccess) kern<<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);

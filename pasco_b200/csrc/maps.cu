@@ -37,9 +37,14 @@ extern "C" int pasco_device_info(int* sm_count, int* smem_optin, int* cc) {
 // hash table
 // ------------------------------------------------------------------------------------------------
 __global__ void k_hash_insert(const int4* __restrict__ coords, int64_t n, unsigned long long* keys, int* vals,
-                              uint32_t mask) {
+                              uint32_t mask, int* __restrict__ err) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int4 c = __ldg(coords + i);
+    // keys pack 16 bits per component (bias 2^15): a component outside [-32768, 32767] would alias another voxel, and
+    // (32767,32767,32767,32767) is the empty-slot marker.  Flag it (the host raises) instead of mapping silently.
+    const bool bad = ((unsigned)(c.x + kCoordBias) | (unsigned)(c.y + kCoordBias) | (unsigned)(c.z + kCoordBias) |
+                      (unsigned)(c.w + kCoordBias)) > 0xFFFFu;
+    if (err && (bad || pack_key(c.x, c.y, c.z, c.w) == kEmptyKey)) *err = 2;
     uint64_t key = pack_key(c.x, c.y, c.z, c.w);
     uint32_t slot = hash_key(key) & mask;
     while (true) {
@@ -71,7 +76,7 @@ __global__ void k_hash_remap(int32_t* vals, int64_t cap, const int32_t* __restri
 static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 extern "C" int pasco_hash_insert(const int32_t* coords, int64_t n, uint64_t* table_keys, int32_t* table_vals,
-                                 int64_t capacity, int32_t* first_row, pasco_stream_t s) {
+                                 int64_t capacity, int32_t* first_row, int32_t* err_flag, pasco_stream_t s) {
   PASCO_CHECK_ARG(is_pow2(capacity) && capacity >= 2 * n && capacity <= (1ll << 31),
                   "pasco_hash_insert: capacity %lld must be a power of two >= 2n (n=%lld)", (long long)capacity,
                   (long long)n);
@@ -79,7 +84,7 @@ extern "C" int pasco_hash_insert(const int32_t* coords, int64_t n, uint64_t* tab
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)s;
   k_hash_insert<<<grid_for(n, 256), 256, 0, st>>>((const int4*)coords, n, (unsigned long long*)table_keys,
-                                                   table_vals, (uint32_t)(capacity - 1));
+                                                   table_vals, (uint32_t)(capacity - 1), err_flag);
   if (first_row)
     k_hash_lookup<<<grid_for(n, 256), 256, 0, st>>>((const int4*)coords, n, table_keys, table_vals,
                                                      (uint32_t)(capacity - 1), first_row);

@@ -69,8 +69,12 @@ def raise_pending_errors(dev=None) -> None:
     for d, f in list(_ERR.items()):
         if dev is not None and d != dev:
             continue
-        if int(f.item()) != 0:
+        code = int(f.item())
+        if code != 0:
             f.zero_()
+            if code == 2:
+                raise RuntimeError("pasco_b200: a coordinate or batch index lies outside [-32768, 32767] "
+                                   "(coordinate keys pack 16 bits per component)")
             raise RuntimeError("pasco_b200: a coordinate lies outside the requested dense volume "
                                "(SparseTensor.dense / to_sparse: check min_coordinate and shape)")
 
@@ -105,7 +109,7 @@ def hash_insert(coords: torch.Tensor) -> Tuple[HashTable, torch.Tensor]:
     keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)                 # 0xFF… = empty
     vals = torch.full((cap,), 0x7F7F7F7F, dtype=torch.int32, device=dev)
     first = torch.empty(n, dtype=torch.int32, device=dev)
-    call("pasco_hash_insert", ptr(coords), n, ptr(keys), ptr(vals), cap, ptr(first))
+    call("pasco_hash_insert", ptr(coords), n, ptr(keys), ptr(vals), cap, ptr(first), ptr(_err_flag(dev)))
     return HashTable(keys, vals), first
 
 
@@ -347,12 +351,6 @@ class PackedWeights:
         return buf
 
 
-def set_conv_variant(variant: int) -> None:
-    """0 (default) = register-gather conv kernel, 1 = TMA-gather kernel where eligible (Cout <= 128)."""
-    if load().pasco_conv_set_variant(int(variant)) != 0:
-        raise RuntimeError(load().pasco_last_error().decode())
-
-
 def use_planes(flag: bool) -> None:
     global _USE_PLANES
     _USE_PLANES = bool(flag)
@@ -401,7 +399,9 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
     _PENDING_STATS = None            # statistics of an earlier launch never survive another convolution
     use_tc = _tc_ok(c_contract, c_out, kk, "dgrad" if transpose_w else "fwd")
     split_k = use_tc and _SPLIT_K and load().pasco_conv_splitk_workspace_bytes(kk, n_out, c_out) > 0
+    path = "simt"
     if use_tc and not split_k and _planes_ok(c_contract, kk, nbr):
+        path = "planes"
         hi, lo = planes if planes is not None else split_planes(feats, in_scale, in_shift, in_act)
         if planes_out is not None:
             planes_out.append((hi, lo))
@@ -414,11 +414,13 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         if stats is not None:
             _PENDING_STATS = (weakref.ref(out), out.data_ptr(), out._version, tuple(out.shape), stats)
     elif use_tc and _SPLIT_K and (ws_bytes := load().pasco_conv_splitk_workspace_bytes(kk, n_out, c_out)) > 0:
+        path = "splitk"
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=feats.device)
         call("pasco_conv_forward_splitk", ptr(feats), feats.shape[0], ptr(nbr), kk, n_out, c_contract, c_out,
              ptr((packs or PackedWeights()).get(weight, transpose_w)), koff_arr, ptr(bias), ptr(in_scale), ptr(in_shift), in_act,
              ptr(out), _PRECISION, 0, 0, ptr(ws), ws_bytes)
     elif use_tc:
+        path = "regs"
         stats = None
         if want_stats and _FUSE_BN_STATS and n_out >= 4096:
             stats = torch.zeros(2, c_out, dtype=torch.float64, device=feats.device)
@@ -439,7 +441,7 @@ def conv_apply(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Te
         prof.append(("dgrad" if transpose_w else "fwd", ev0, ev1,
                      dict(n_in=feats.shape[0], n_out=n_out, K=kk, Cin=c_contract, Cout=c_out,
                           pairs=PAIR_COUNTS.get(nbr.data_ptr()) if nbr is not None else None,
-                          tc=use_tc, precision=_PRECISION)))
+                          tc=use_tc, precision=_PRECISION, path=path)))
     return out
 
 
@@ -480,6 +482,7 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
     tc = _tc_ok(Cin, 64, 1, "wgrad") and Cin % 64 == 0 and Cout % 64 == 0 and Cout <= 256
+    path = "planes" if tc and _planes_ok(Cin, K, nbr) else ("regs" if tc else "simt")
     if tc and _planes_ok(Cin, K, nbr):
         ih, il = in_planes if in_planes is not None else split_planes(feats, in_scale, in_shift, in_act)
         gh, gl = g_planes if g_planes is not None else split_planes(gout)
@@ -498,7 +501,7 @@ def conv_wgrad(feats: torch.Tensor, gout: torch.Tensor, nbr: Optional[torch.Tens
         ev1.record()
         prof.append(("wgrad", ev0, ev1, dict(n_in=feats.shape[0], n_out=n_out, K=K, Cin=Cin, Cout=Cout,
                                              pairs=PAIR_COUNTS.get(nbr.data_ptr()) if nbr is not None else None,
-                                             tc=True, precision=_PRECISION)))
+                                             tc=tc, precision=_PRECISION, path=path)))
     return dW
 
 

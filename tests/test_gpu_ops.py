@@ -281,54 +281,6 @@ def test_conv_plane_and_register_gather_are_bit_identical(prec, cin, cout):
     assert res[0][0].abs().sum() > 0
 
 
-@pytest.mark.parametrize("kind,cin,cout", [("k3", 64, 64), ("k3", 128, 128), ("down", 64, 128), ("up", 128, 64)])
-def test_conv_tma_gather_variant(ME, kind, cin, cout):
-    """Variant 1 of pasco_conv_forward_tc: neighbour rows fetched by TMA tile::gather4 into a raw ring, warps convert."""
-    from pasco_b200 import ops
-    ops.set_precision("fp32")
-    ops.set_conv_variant(1)
-    ops.use_planes(False)
-    try:
-        _run_conv_case(ME, kind, cin, cout, TOL_TIGHT)
-    finally:
-        ops.set_conv_variant(0)
-        ops.use_planes(True)
-
-
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_conv_tma_and_register_gather_are_bit_identical(prec):
-    """Same operand split, same MMA order → the two kernels must agree bit for bit (incl. the fused BN prologue,
-    missing neighbours, a ragged last tile and a pitched input)."""
-    from pasco_b200 import ops
-    ops.set_precision(prec)
-    g = torch.Generator().manual_seed(3)
-    occ = torch.rand(40, 36, 12, generator=g) < 0.3
-    c = torch.nonzero(occ).int()
-    C = torch.cat([torch.zeros(c.shape[0], 1, dtype=torch.int32), c], 1).cuda()
-    N = C.shape[0]
-    table, _ = ops.hash_insert(C)
-    nbr = ops.kernel_map_probe(C, table, 3, (1, 1, 1))
-    wide = torch.randn(N, 192, generator=g).cuda()
-    F = wide[:, 64:128]                                  # pitched view: 64 channels out of 192
-    W = (torch.randn(27, 64, 128, generator=g) * 0.05).cuda()
-    scale, shift = torch.rand(64, generator=g).cuda() + 0.5, torch.randn(64, generator=g).cuda()
-    outs = []
-    ops.use_planes(False)
-    try:
-        for variant in (1, 0):
-            ops.set_conv_variant(variant)
-            pk = ops.PackedWeights()
-            a = ops.conv_apply(F.contiguous(), W, nbr, N, False, None, packs=pk)
-            b = ops.conv_apply(F.contiguous(), W, nbr, N, False, None, in_scale=scale, in_shift=shift, in_act=1, packs=pk)
-            outs.append((a, b))
-    finally:
-        ops.set_conv_variant(0)
-        ops.use_planes(True)
-        ops.set_precision("fp32")
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    assert outs[0][0].abs().sum() > 0
-
-
 @pytest.mark.parametrize("cin,cout,bias", [(64, 64, False), (64, 128, True), (128, 256, False), (64, 48, True)])
 def test_conv_epilogue_statistics(cin, cout, bias):
     """Fused BatchNorm statistics: the conv epilogue's column sums / sums of squares of its output (incl. bias, a ragged
