@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import itertools
 import math
+import os
+import sys
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -233,6 +235,19 @@ class TensorField:
     """Referenced only in isinstance checks (pasco/models/dropout.py:23,47)."""
 
 
+_HOOKS_PENDING = os.environ.get("PASCO_B200_HOOKS", "0") == "1"
+
+
+def _maybe_install_hooks() -> None:
+    """PASCO_B200_HOOKS=1: once the reference's transformer module has been imported, route its cross-attention and
+    attention-mask construction onto the engine (pasco_b200/hooks.py).  Checked when a SparseTensor is built."""
+    global _HOOKS_PENDING
+    if _HOOKS_PENDING and "pasco.models.transformer.transformer_predictor_v2" in sys.modules:
+        _HOOKS_PENDING = False
+        from .. import hooks
+        hooks.install()
+
+
 class _LazyRows:
     """Deferred act(BatchNorm(x)) over rows — what MinkowskiBatchNorm (+ a following MinkowskiReLU / LeakyReLU) returns in
     training mode.  If the consumer is a stride-1 k>1 MinkowskiConvolution the three run as ONE fused node whose
@@ -267,6 +282,8 @@ class SparseTensor:
                  allocator_type=None, minkowski_algorithm=None, requires_grad=None, device=None):
         if not (isinstance(features, (torch.Tensor, _LazyRows)) and features.ndim == 2):
             raise ValueError("features must be a [N, C] tensor")
+        if _HOOKS_PENDING:
+            _maybe_install_hooks()
         if coordinate_map_key is None:
             if coordinates is None:
                 raise ValueError("either coordinates or coordinate_map_key is required")

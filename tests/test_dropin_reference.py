@@ -105,6 +105,36 @@ def test_unmodified_reference_net_on_the_engine_matches_golden_and_pasconet():
         assert err <= 1e-3
 
 
+def test_reference_with_attention_hooks_matches_golden():
+    """pasco_b200.hooks.install(): the unmodified reference's CrossAttentionLayer / compute_attn_mask run on the xattn
+    kernels and the sparse mask instead of nn.MultiheadAttention and the dense [100, X, Y, Z] volume — same golden."""
+    from pasco_b200 import ops, hooks
+    from pasco_b200.synthetic import make_scene
+    ops.set_precision("fp32")
+    man = json.load(open(os.path.join(HERE, "golden", "net_cfg1_manifest.json")))
+    gold = np.load(os.path.join(HERE, "golden", "net_cfg1.npz"))
+    dev = torch.device("cuda")
+    ME, net = _reference_net()
+    net.load_state_dict(fill_state_dict(net.state_dict()))
+    net.to(dev).train()
+    assert hooks.install()
+    try:
+        b = make_scene(man["grid"], man["occ"], 1, seed=man["seed"])
+        out = _forward_reference(ME, net, b, dev)
+        p = out["panop_predictions"][0]
+        report = {"vox": _compare("voxel_logits", p["voxel_logits"].C, p["voxel_logits"].F, gold["vox_C"], gold["vox_F"], man["row_step"]),
+                  "query": _rel(p["query_logits"][0], gold["query_logits"])}
+        assert report["query"] <= 1e-3, report
+        for i, aux in enumerate(p["aux_outputs"]):
+            assert _rel(aux["query_logits"][0], gold[f"aux{i}_query_logits"]) <= 1e-3
+        (p["voxel_logits"].F.square().mean() + p["query_logits"].square().mean()).backward()
+        g = net.transformer_predictor.transformer_cross_attention_layers[1].multihead_attn.in_proj_weight.grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+        print("drop-in with attention hooks vs golden:", report)
+    finally:
+        hooks.uninstall()
+
+
 def _keys_of(C):
     c = C.long().cpu()
     return ((c[:, 0] + 32768) << 48) | ((c[:, 1] + 32768) << 32) | ((c[:, 2] + 32768) << 16) | (c[:, 3] + 32768)
