@@ -684,6 +684,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
       }
       return r;
     };
+    // Every producer warp OBSERVES the "empty" barrier of every slot in order and fills only its own.  (Waiting only on
+    // one's own slots is wrong when the ring is shorter than the warp stride: a parity wait cannot tell "completed once
+    // more" from "not completed yet", so a warp must never be two ring revolutions ahead of a barrier it waits on.)
     It it0, it1, it2;
     enter(it0, blockIdx.x);
     advance_n(it0, warp);
@@ -692,15 +695,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
     it2 = it1;
     advance_n(it2, NUM_GATHER_WARPS);
     Idx4 q0 = load_idx(it0), q1 = load_idx(it1);
-    int n = warp;                                   // slot number in the CTA's sequence
     const uint8_t* base_hi = reinterpret_cast<const uint8_t*>(p.pl_hi);
     const uint8_t* base_lo = reinterpret_cast<const uint8_t*>(p.pl_lo);
     const int64_t pitch_b = p.pl_pitch * 2;
+    int stage = 0;                                  // ring position of the slot being observed
+    uint32_t phase = 0;
+    auto observe = [&]() {                          // wait until the current slot's stage is free, then move on
+      mbar_wait(smem_u32(aempty + stage), phase ^ 1);
+    };
+    auto next_stage = [&]() {
+      if (++stage == p.sa) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+    for (int i = 0; i < warp && it0.valid; ++i) {   // the slots before this warp's first one
+      observe();
+      next_stage();
+    }
     while (it0.valid) {
       const Idx4 q2 = load_idx(it2);                // indices of this warp's slot after next
-      const int stage = n % p.sa;
-      const uint32_t parity = (uint32_t)((n / p.sa) & 1);
-      mbar_wait(smem_u32(aempty + stage), parity ^ 1);
+      observe();
       const uint32_t dst0 = smem_u32(a_smem + (size_t)stage * a_stage_bytes) + (uint32_t)sub * 128u;
       const int64_t coff_b = ((int64_t)it0.kb * KBLK + ch * 8) * 2;
 #pragma unroll
@@ -715,10 +730,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
         if (NSPLIT == 3) cp_async16_zfill(dst0 + A_TILE_BYTES + off, base_lo + boff, nbytes);
       }
       cp_async_mbar_arrive_noinc(smem_u32(afull + stage));
-      n += NUM_GATHER_WARPS;
+      next_stage();
       it0 = it1; it1 = it2;
       advance_n(it2, NUM_GATHER_WARPS);
       q0 = q1; q1 = q2;
+      if (it0.valid) {
+        for (int i = 0; i < NUM_GATHER_WARPS - 1; ++i) {   // the other warps' slots up to this warp's next one
+          observe();
+          next_stage();
+        }
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();

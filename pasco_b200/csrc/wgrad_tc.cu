@@ -476,17 +476,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
     const uint8_t* in_lo = reinterpret_cast<const uint8_t*>(p.in_lo);
     const uint8_t* gp_hi = reinterpret_cast<const uint8_t*>(p.g_hi);
     const uint8_t* gp_lo = reinterpret_cast<const uint8_t*>(p.g_lo);
-    int64_t s = warp;
-    Idx4 q0 = load_idx(s);
-    for (; s < total_slots; s += NUM_GATHER_WARPS) {
-      const Idx4 q1 = load_idx(s + NUM_GATHER_WARPS);
-      const int64_t rti = s / spr;
-      const int j = (int)(s - rti * spr);
+    // Every producer warp OBSERVES the "empty" barrier of every slot in order (gout double buffer / unit ring) and fills
+    // only its own slots s ≡ warp (mod 8): a parity wait cannot tell "completed once more" from "not completed yet", so
+    // no warp may get two revolutions ahead of a barrier it waits on.
+    Idx4 q0 = load_idx(warp);
+    int64_t rti = 0;                      // row-tile ordinal of the slot being observed
+    int j = 0;                            // position inside the row tile: 0 = gout tile, 1.. = units
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t s = 0; s < total_slots; ++s) {
+      const bool own = (s % NUM_GATHER_WARPS) == warp;
       const int64_t rt = cta_in_pass + rti * stride_rt;
       if (j == 0) {
         // ---- the gout tile of this row tile: [64 rows][Cout] per plane, contiguous rows ----
         const int gb = (int)(rti & 1);
         mbar_wait(smem_u32(gempty_bar + gb), (uint32_t)(((rti >> 1) & 1) ^ 1));
+        if (own) {
         const uint32_t g0 = smem_u32(g_smem + (size_t)gb * g_bytes) + (uint32_t)sub * 128u;
 #pragma unroll 4
         for (int i = 0; i < WG_R / 4; ++i) {
@@ -500,12 +505,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
           }
         }
         cp_async_mbar_arrive_noinc(smem_u32(gfull_bar + gb));
+        }
       } else {
         // ---- one unit: two gathered [64 rows][64 ch] sub-tiles ----
-        const int64_t ord = rti * nunits + (j - 1);
-        const int stage = (int)(ord % p.stages);
-        const uint32_t parity = (uint32_t)((ord / p.stages) & 1);
-        mbar_wait(smem_u32(empty_bar + stage), parity ^ 1);
+        mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+        if (own) {
         const uint32_t a0 = smem_u32(a_smem + (size_t)stage * a_bytes) + (uint32_t)sub * 128u;
         const int sb0 = (unit0 + (j - 1)) * 2;
 #pragma unroll
@@ -523,8 +527,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
           }
         }
         cp_async_mbar_arrive_noinc(smem_u32(full_bar + stage));
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
-      q0 = q1;
+      if (own) q0 = load_idx(s + NUM_GATHER_WARPS);     // indices of this warp's next slot (8 CTA slots ahead)
+      if (++j == spr) {
+        j = 0;
+        ++rti;
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
