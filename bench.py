@@ -209,7 +209,8 @@ def run_ours(a):
     # every scene of the pool is seen by a warm-up step, so that the caching allocator holds blocks of every size before
     # the timed regions (a first-touch cudaMalloc synchronises the device)
     n_pool = max(1, min(a.pool, a.warmup * ACC))
-    host_scenes = [pin(make_scene(GRID, OCC, M, IN_CH, N_CLASSES, seed=sd)) for sd in parallel.scene_seeds(rank, world, n_pool)]
+    host_scenes = [pin(make_scene(GRID, OCC, M, IN_CH, N_CLASSES, seed=sd, clustered=a.occupancy == "clustered"))
+                   for sd in parallel.scene_seeds(rank, world, n_pool)]
     dev_scenes = [to_device(s, dev) for s in host_scenes]
     torch.cuda.synchronize()
     # the reference's DDP gradient averaging (scripts/train.py:213): 64 MB buckets all-reduced while backward continues
@@ -378,10 +379,10 @@ def run_ours(a):
 
     if rank == 0:
         scenes_per_step = world * ACC * M          # a MIMO group holds M scenes (one per subnet), ACC groups per optimiser step
-        default_mode = a.shape == "semkitti" and M == 1 and ACC == 1 and not a.heavy_decoder
+        default_mode = a.shape == "semkitti" and M == 1 and ACC == 1 and not a.heavy_decoder and a.occupancy == "uniform"
         workload = ("configs[1] shape: 256x256x32 @10% occ, full PaSCo (Net3D + MaskPLS 100 queries, M=1, f=64), "
                     "fwd+bwd+AdamW, 1 scene/GPU/step, train-mode caps 25k/120k/400k") if default_mode else (
-            f"256x256x32 @{OCC:.0%} occ {a.shape} shape ({N_CLASSES} classes, {IN_CH}-wide point features), full PaSCo M={M}"
+            f"256x256x32 @{OCC:.0%} occ ({a.occupancy}) {a.shape} shape ({N_CLASSES} classes, {IN_CH}-wide point features), full PaSCo M={M}"
             f"{' heavy decoder' if a.heavy_decoder else ''}, f=64, fwd+bwd+AdamW, {ACC} MIMO group(s) of {M} scene(s) per GPU per "
             f"optimiser step (gradient accumulation), global batch {scenes_per_step} scenes")
         line = {"metric": METRIC, "value": round(scenes_per_step * a.steps / (ms / 1e3), 4), "unit": "scenes/s", "n_gpus": world,
@@ -467,6 +468,8 @@ if __name__ == "__main__":
     ap.add_argument("--m", type=int, default=1, help="MIMO subnets per network (n_infers); a step then covers M scenes per group")
     ap.add_argument("--accum", type=int, default=1, help="MIMO groups per GPU per optimiser step (gradient accumulation)")
     ap.add_argument("--heavy-decoder", action="store_true")
+    ap.add_argument("--occupancy", default="uniform", choices=["uniform", "clustered"],
+                    help="uniform = Bernoulli occupancy (BASELINE configs); clustered = ground slab + boxes, same voxel count")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient all-reduce bucket size (N > 1)")
