@@ -15,7 +15,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpasco_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DPASCO_NO_FAST_MATH"]
+         "-Xcompiler", "-fPIC", "-DPASCO_NO_FAST_MATH"] + os.environ.get("PASCO_NVCC_FLAGS", "").split()
 
 
 def _stale(target: str, deps) -> bool:

@@ -684,35 +684,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
       }
       return r;
     };
-    // Every producer warp OBSERVES the "empty" barrier of every slot in order and fills only its own.  (Waiting only on
-    // one's own slots is wrong when the ring is shorter than the warp stride: a parity wait cannot tell "completed once
-    // more" from "not completed yet", so a warp must never be two ring revolutions ahead of a barrier it waits on.)
+    // Ownership: W = min(8, sa) producer warps are active and warp w fills the slots n = w, w + W, w + 2W, ...  A warp
+    // waits only on the "empty" barriers of its own slots; the parity wait is sound because its previous wait (slot
+    // n - W) already required slot n - W - sa >= n - 2 sa to be consumed (W <= sa), so it is never two ring revolutions
+    // ahead of the barrier, and it cannot be behind it either (the next completion needs this very slot filled).
+    // (Two earlier variants deadlocked: a stride of 8 with a ring of 6 lets a warp run two revolutions ahead; letting
+    // every warp observe every slot's barrier fails the other way round — a slow observer falls a revolution BEHIND
+    // and then waits for a completion that depends on its own slot.  tools/pipeline_sim.py replays both.)
+    const int W = NUM_GATHER_WARPS < p.sa ? NUM_GATHER_WARPS : p.sa;
     It it0, it1, it2;
     enter(it0, blockIdx.x);
+    if (warp >= W) it0.valid = false;
     advance_n(it0, warp);
     it1 = it0;
-    advance_n(it1, NUM_GATHER_WARPS);
+    advance_n(it1, W);
     it2 = it1;
-    advance_n(it2, NUM_GATHER_WARPS);
+    advance_n(it2, W);
     Idx4 q0 = load_idx(it0), q1 = load_idx(it1);
     const uint8_t* base_hi = reinterpret_cast<const uint8_t*>(p.pl_hi);
     const uint8_t* base_lo = reinterpret_cast<const uint8_t*>(p.pl_lo);
     const int64_t pitch_b = p.pl_pitch * 2;
-    int stage = 0;                                  // ring position of the slot being observed
+    int stage = warp;                               // ring position of this warp's current slot (warp < W <= sa)
     uint32_t phase = 0;
-    auto observe = [&]() {                          // wait until the current slot's stage is free, then move on
+    auto observe = [&]() {                          // wait until the slot's stage is free
       mbar_wait(smem_u32(aempty + stage), phase ^ 1);
     };
-    auto next_stage = [&]() {
-      if (++stage == p.sa) {
-        stage = 0;
+    auto next_stage = [&]() {                       // this warp's next slot is W slots on (at most one wrap: W <= sa)
+      stage += W;
+      if (stage >= p.sa) {
+        stage -= p.sa;
         phase ^= 1;
       }
     };
-    for (int i = 0; i < warp && it0.valid; ++i) {   // the slots before this warp's first one
-      observe();
-      next_stage();
-    }
     while (it0.valid) {
       const Idx4 q2 = load_idx(it2);                // indices of this warp's slot after next
       observe();
@@ -732,14 +735,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
       cp_async_mbar_arrive_noinc(smem_u32(afull + stage));
       next_stage();
       it0 = it1; it1 = it2;
-      advance_n(it2, NUM_GATHER_WARPS);
+      advance_n(it2, W);
       q0 = q1; q1 = q2;
-      if (it0.valid) {
-        for (int i = 0; i < NUM_GATHER_WARPS - 1; ++i) {   // the other warps' slots up to this warp's next one
-          observe();
-          next_stage();
-        }
-      }
     }
     cp_async_commit();
     cp_async_wait<0>();

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace umma {
 
@@ -34,10 +35,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef PASCO_HANG_TRAP
+// debug build (PASCO_NVCC_FLAGS=-DPASCO_HANG_TRAP python -m pasco_b200.build --force): a wait that spins for ~1 s reports
+// who waits on what and traps, so that a pipeline deadlock shows up as an error with a location instead of a hang
+static __device__ __noinline__ void mbar_wait_report(uint32_t bar, uint32_t parity) {
+  printf("HANG block %d thread %d (warp %d) waits on smem barrier 0x%x parity %u\n", blockIdx.x, threadIdx.x, threadIdx.x >> 5, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  unsigned long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1ull << 17)) mbar_wait_report(bar, parity);
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
 
 // ---- async-proxy visibility of generic st.shared writes ------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -442,56 +442,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
   const int spr = 1 + nunits;                // slots per row tile: the gout tile, then one per unit
 
   if (warp < NUM_GATHER_WARPS) {
-    // ONE WARP PER SLOT: the CTA's slot sequence is (row tile → [gout tile, unit 0, unit 1, ...]); warp w fills the slots
-    // s ≡ w (mod 8), every row of them.  lane = (row sub-index 0..3, 16-byte chunk 0..7): one copy instruction moves 4
-    // tile rows.  For a unit slot lane l holds the neighbour indices of rows l and l+32 of both sub-tiles (four coalesced
-    // 128-byte loads, fetched one of the warp's slots = 8 CTA slots ahead), distributed by one shuffle per instruction.
+    // ONE WARP PER SLOT, ownership split by resource:
+    //   * warp 7 fills every gout tile (double buffer; consecutive fills by the same warp, so its parity wait on the
+    //     "gout empty" barrier is never more than one phase away from the barrier);
+    //   * warps 0 .. Wu-1 (Wu = min(7, stages)) fill the unit slots ord = w, w + Wu, ... of the CTA's unit sequence
+    //     (row tile major): the stride Wu <= stages keeps a warp within one revolution of the unit ring.
+    // A warp waits only on barriers of slots it owns.  (Letting all 8 warps take slots round-robin across both rings, or
+    // letting every warp observe every barrier, deadlocks: a parity wait is only sound when the waiter is neither two
+    // revolutions ahead of nor one revolution behind the barrier — tools/pipeline_sim.py replays the three schemes.)
+    // lane = (row sub-index 0..3, 16-byte chunk 0..7): one copy instruction moves 4 tile rows.  For a unit slot lane l
+    // holds the neighbour indices of rows l and l+32 of both sub-tiles (four coalesced 128-byte loads, fetched one of
+    // the warp's slots ahead), distributed by one shuffle per instruction.
     const int ch = lane & 7, sub = lane >> 3;
     const int64_t stride_rt = p.ctas_per_pass;
     const int64_t my_rts = cta_in_pass < num_rt ? (num_rt - cta_in_pass + stride_rt - 1) / stride_rt : 0;   // row tiles of this CTA
-    const int64_t total_slots = my_rts * spr;
-    struct Idx4 { int v[4]; };                      // [sub-tile h][row half]
-    auto load_idx = [&](int64_t s) -> Idx4 {
-      Idx4 r;
-      r.v[0] = r.v[1] = r.v[2] = r.v[3] = -1;
-      if (s < total_slots) {
-        const int64_t rt = cta_in_pass + (s / spr) * stride_rt;
-        const int j = (int)(s % spr);
-        if (j > 0) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int sbi = (unit0 + (j - 1)) * 2 + h;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int64_t row = rt * WG_R + q * 32 + lane;
-              if (sbi < p.num_subs && row < p.n_out)
-                r.v[h * 2 + q] = p.nbr ? __ldg(p.nbr + (int64_t)(sbi / CB) * p.n_out + row) : (int)row;
-            }
-          }
-        }
-      }
-      return r;
-    };
     const uint8_t* in_hi = reinterpret_cast<const uint8_t*>(p.in_hi);
     const uint8_t* in_lo = reinterpret_cast<const uint8_t*>(p.in_lo);
     const uint8_t* gp_hi = reinterpret_cast<const uint8_t*>(p.g_hi);
     const uint8_t* gp_lo = reinterpret_cast<const uint8_t*>(p.g_lo);
-    // Every producer warp OBSERVES the "empty" barrier of every slot in order (gout double buffer / unit ring) and fills
-    // only its own slots s ≡ warp (mod 8): a parity wait cannot tell "completed once more" from "not completed yet", so
-    // no warp may get two revolutions ahead of a barrier it waits on.
-    Idx4 q0 = load_idx(warp);
-    int64_t rti = 0;                      // row-tile ordinal of the slot being observed
-    int j = 0;                            // position inside the row tile: 0 = gout tile, 1.. = units
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t s = 0; s < total_slots; ++s) {
-      const bool own = (s % NUM_GATHER_WARPS) == warp;
-      const int64_t rt = cta_in_pass + rti * stride_rt;
-      if (j == 0) {
-        // ---- the gout tile of this row tile: [64 rows][Cout] per plane, contiguous rows ----
+    const int Wu = (NUM_GATHER_WARPS - 1) < p.stages ? (NUM_GATHER_WARPS - 1) : p.stages;
+    if (warp == NUM_GATHER_WARPS - 1) {
+      // ---- gout tiles: [64 rows][Cout] per plane, contiguous rows ----
+      for (int64_t rti = 0; rti < my_rts; ++rti) {
+        const int64_t rt = cta_in_pass + rti * stride_rt;
         const int gb = (int)(rti & 1);
         mbar_wait(smem_u32(gempty_bar + gb), (uint32_t)(((rti >> 1) & 1) ^ 1));
-        if (own) {
         const uint32_t g0 = smem_u32(g_smem + (size_t)gb * g_bytes) + (uint32_t)sub * 128u;
 #pragma unroll 4
         for (int i = 0; i < WG_R / 4; ++i) {
@@ -505,13 +480,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
           }
         }
         cp_async_mbar_arrive_noinc(smem_u32(gfull_bar + gb));
+      }
+    } else if (warp < Wu) {
+      // ---- units: two gathered [64 rows][64 ch] sub-tiles each ----
+      const int64_t total_units = my_rts * nunits;
+      struct Idx4 { int v[4]; };                    // [sub-tile h][row half]
+      auto load_idx = [&](int64_t ord) -> Idx4 {
+        Idx4 r;
+        r.v[0] = r.v[1] = r.v[2] = r.v[3] = -1;
+        if (ord < total_units) {
+          const int64_t rt = cta_in_pass + (ord / nunits) * stride_rt;
+          const int u = (int)(ord % nunits);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int sbi = (unit0 + u) * 2 + h;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int64_t row = rt * WG_R + q * 32 + lane;
+              if (sbi < p.num_subs && row < p.n_out)
+                r.v[h * 2 + q] = p.nbr ? __ldg(p.nbr + (int64_t)(sbi / CB) * p.n_out + row) : (int)row;
+            }
+          }
         }
-      } else {
-        // ---- one unit: two gathered [64 rows][64 ch] sub-tiles ----
+        return r;
+      };
+      int stage = warp;                             // warp < Wu <= stages
+      uint32_t phase = 0;
+      Idx4 q0 = load_idx(warp);
+      for (int64_t ord = warp; ord < total_units; ord += Wu) {
+        const Idx4 q1 = load_idx(ord + Wu);         // indices of this warp's next unit
+        const int u = (int)(ord % nunits);
         mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-        if (own) {
         const uint32_t a0 = smem_u32(a_smem + (size_t)stage * a_bytes) + (uint32_t)sub * 128u;
-        const int sb0 = (unit0 + (j - 1)) * 2;
+        const int sb0 = (unit0 + u) * 2;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int sbi = sb0 + h;
@@ -527,16 +528,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
           }
         }
         cp_async_mbar_arrive_noinc(smem_u32(full_bar + stage));
-        }
-        if (++stage == p.stages) {
-          stage = 0;
+        stage += Wu;                                // at most one wrap: Wu <= stages
+        if (stage >= p.stages) {
+          stage -= p.stages;
           phase ^= 1;
         }
-      }
-      if (own) q0 = load_idx(s + NUM_GATHER_WARPS);     // indices of this warp's next slot (8 CTA slots ahead)
-      if (++j == spr) {
-        j = 0;
-        ++rti;
+        q0 = q1;
       }
     }
     cp_async_commit();

@@ -12,6 +12,11 @@ for S in $STEPS; do
       timeout 150 python tools/debug_planes.py > $O/${TAG}_dbg.log 2>&1; rc=$?
       grep -c "equal: True" $O/${TAG}_dbg.log; grep "False\|Error\|error" $O/${TAG}_dbg.log | head -5
       if [ $rc -ne 0 ]; then echo "debug step failed/hung (rc=$rc): stopping"; tail -5 $O/${TAG}_dbg.log; exit 1; fi ;;
+    trap)
+      PASCO_NVCC_FLAGS=-DPASCO_HANG_TRAP python -m pasco_b200.build --force > $O/${TAG}_trapbuild.log 2>&1
+      timeout 200 python tools/debug_planes.py wgrad > $O/${TAG}_trap.log 2>&1
+      grep "HANG" $O/${TAG}_trap.log | sort | uniq -c | sort -rn | head -40; tail -5 $O/${TAG}_trap.log | cut -c1-300
+      python -m pasco_b200.build --force > /dev/null 2>&1 ;;
     micro)
       timeout 200 python tools/conv_microbench.py --occ 0.5 0.1 --channels 64 128 256 --out $O/${TAG}_micro.jsonl 2>&1 | grep conv3 | python -c "
 import sys, json
