@@ -439,7 +439,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int spr = 1 + nunits;                // slots per row tile: the gout tile, then one per unit
 
   if (warp < NUM_GATHER_WARPS) {
     // ONE WARP PER SLOT, ownership split by resource:
