@@ -172,8 +172,13 @@ __device__ __forceinline__ void role_weight_loader(const ConvParams& p, const Pi
 }
 
 // one thread: tcgen05.mma (M=128, N=Cout, K=16) into the tile's TMEM accumulator; commits free the A / B ring slots
+// `nm` issuer threads (one per warp) share the work: issuer `mid` owns the tiles t ≡ mid (mod nm) of every group — tiles
+// of a group accumulate into different TMEM columns, so their MMAs are independent.  One issuer needs ~100 cycles of
+// descriptor / uniform-register work per tcgen05.mma while an M=128, N=64 MMA executes in 32: with a single issuer the
+// tensor pipe idled at 30 % (ncu: the issuer thread busy on every instruction of its loop, producers waiting for stages).
+// The "B stage free" and "accumulators ready" barriers expect one commit per issuer.
 template <int NSPLIT, bool CPASYNC_A = false>
-__device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
+__device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl, int mid = 0, int nm = 1) {
   const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.Cout, 0, 0);
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;
@@ -191,6 +196,7 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
         mbar_wait(smem_u32(pl.bfull + sb), pb);
         const uint32_t b_hi = smem_u32(pl.b_smem + (size_t)sb * pl.b_stage_bytes), b_lo = b_hi + pl.b_tile;
         for (int t = 0; t < t_eff; ++t) {
+          if (t % nm == mid) {
           mbar_wait(smem_u32(pl.afull + sa), pa);
           if (CPASYNC_A) fence_proxy_async_smem();   // the A stage was written by cp.async copies (generic proxy)
           tc_fence_after();
@@ -210,6 +216,7 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl) {
             }
           }
           mma_commit(smem_u32(pl.aempty + sa));
+          }
           if (++sa == p.sa) {
             sa = 0;
             pa ^= 1;
@@ -578,8 +585,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+constexpr int PL_MMA_WARPS = 4;                                      // tcgen05.mma issuers (one thread each), see role_mma
+constexpr int PL_MMA_WARP0 = LOAD_WARP + 1;                          // issuer 0 = MMA_WARP, issuers 1..3 = warps 14..16
+constexpr int NUM_THREADS_PL = (PL_MMA_WARP0 + PL_MMA_WARPS - 1) * 32;   // 544
+
 template <int NSPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(NUM_THREADS_PL, 1) k_conv_pl(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int n_op = (NSPLIT == 3) ? 2 : 1;
@@ -605,17 +616,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
   const int64_t num_groups = (num_tiles + T - 1) / T;
   const int acc_cols = T * p.Cout;
 
+  const int n_mma = T < PL_MMA_WARPS ? T : PL_MMA_WARPS;          // active issuers: one per tile of a group, at most 4
   if (stat_acc)
-    for (int i = threadIdx.x; i < 2 * p.Cout; i += NUM_THREADS) stat_acc[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += NUM_THREADS_PL) stat_acc[i] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(smem_u32(afull + s), 32);   // one cp.async arrival per lane of the warp that fills the slot
       mbar_init(smem_u32(aempty + s), 1);
       mbar_init(smem_u32(bfull + s), 1);
-      mbar_init(smem_u32(bempty + s), 1);
+      mbar_init(smem_u32(bempty + s), n_mma);   // one commit per issuer
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(tfull + b), 1);
+      mbar_init(smem_u32(tfull + b), n_mma);
       mbar_init(smem_u32(tempty + b), NUM_EPI_WARPS);
     }
     fence_barrier_init();
@@ -743,7 +755,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_pl(const __grid_constan
   } else if (warp == LOAD_WARP) {
     if (lane == 0) role_weight_loader(p, pl);
   } else if (warp == MMA_WARP) {
-    if (lane == 0) role_mma<NSPLIT, true>(p, pl);
+    if (lane == 0) role_mma<NSPLIT, true>(p, pl, 0, n_mma);
+  } else if (warp >= PL_MMA_WARP0) {
+    const int mid = warp - PL_MMA_WARP0 + 1;
+    if (lane == 0 && mid < n_mma) role_mma<NSPLIT, true>(p, pl, mid, n_mma);
   } else {
     role_epilogue(p, pl, warp - NUM_GATHER_WARPS, lane);
   }
@@ -959,7 +974,7 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   const int grid = (int)(groups < num_sms() ? groups : num_sms());
   auto launch = [&](auto kern) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err == cudaSuccess) kern<<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+    if (err == cudaSuccess) kern<<<grid, NUM_THREADS_PL, smem, (cudaStream_t)s>>>(p);
     return err;
   };
   const cudaError_t e = precision == 3 ? launch(k_conv_pl<3>) : launch(k_conv_pl<1>);

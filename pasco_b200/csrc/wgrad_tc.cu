@@ -396,8 +396,11 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+constexpr int WG_MMA_WARPS = 4;                                   // tcgen05.mma issuers of k_wgrad_pl (warps 8..11)
+constexpr int NUM_THREADS_WPL = (MMA_WARP + WG_MMA_WARPS) * 32;   // 384
+
 template <int NSPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_constant__ WgradPlParams p) {
+__global__ void __launch_bounds__(NUM_THREADS_WPL, 1) k_wgrad_pl(const __grid_constant__ WgradPlParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int n_op = (NSPLIT == 3) ? 2 : 1;
@@ -422,6 +425,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
   const int nunits = min(p.units_per_pass, p.num_units - unit0);
   const int64_t num_rt = (p.n_out + WG_R - 1) / WG_R;
 
+  // MMA issuers: the units of a row tile accumulate into different TMEM columns, so issuer `mid` (one thread of warp
+  // 8 + mid) owns the units u ≡ mid (mod n_mma); one issuer alone needs ~100 cycles of descriptor work per tcgen05.mma
+  // that executes in 32 (N = 64) and left the tensor pipe at 33 %
+  const int n_mma = nunits < WG_MMA_WARPS ? nunits : WG_MMA_WARPS;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(full_bar + s), 32);    // one cp.async arrival per lane of the warp that fills the slot
@@ -429,9 +436,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(gfull_bar + b), 32);
-      mbar_init(smem_u32(gempty_bar + b), 1);
+      mbar_init(smem_u32(gempty_bar + b), n_mma);     // one commit per MMA issuer
     }
-    mbar_init(smem_u32(done_bar), 1);
+    mbar_init(smem_u32(done_bar), n_mma);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -563,7 +570,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp >= MMA_WARP && warp - MMA_WARP < n_mma) {
+    const int mid = warp - MMA_WARP;
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
       int stage = 0;
@@ -577,6 +585,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
         const uint32_t g_hi = smem_u32(g_smem + (size_t)gb * g_bytes);
         const uint32_t g_lo = g_hi + NB * WG_SUB_BYTES;
         for (int u = 0; u < nunits; ++u) {
+          if (u % n_mma == mid) {
           mbar_wait(smem_u32(full_bar + stage), phase);
           fence_proxy_async_smem();
           tc_fence_after();
@@ -597,6 +606,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_wgrad_pl(const __grid_consta
             }
           }
           mma_commit(smem_u32(empty_bar + stage));
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -727,10 +737,10 @@ extern "C" int pasco_conv_wgrad_planes(const void* in_hi, const void* in_lo, int
   cudaError_t e;
   if (precision == 3) {
     e = cudaFuncSetAttribute(k_wgrad_pl<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_wgrad_pl<3><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+    if (e == cudaSuccess) k_wgrad_pl<3><<<grid, NUM_THREADS_WPL, smem, (cudaStream_t)s>>>(p);
   } else {
     e = cudaFuncSetAttribute(k_wgrad_pl<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_wgrad_pl<1><<<grid, NUM_THREADS, smem, (cudaStream_t)s>>>(p);
+    if (e == cudaSuccess) k_wgrad_pl<1><<<grid, NUM_THREADS_WPL, smem, (cudaStream_t)s>>>(p);
   }
   if (e != cudaSuccess) {
     set_error("pasco_conv_wgrad_planes: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
