@@ -188,7 +188,8 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl, in
     const int64_t group = v / p.ksplit;
     const int k0 = (int)(v % p.ksplit) * p.kchunk, k1 = k0 + p.kchunk < p.K ? k0 + p.kchunk : p.K;
     const int64_t rem = pl.num_tiles - group * pl.T;
-    const int t_eff = rem < pl.T ? (int)rem : pl.T;
+    const int t_eff = pl.T;        // the last group is padded to T tiles (rows >= n_out: never gathered, never stored)
+    (void)rem;
     mbar_wait(smem_u32(pl.tempty + buf), ((it >> 1) & 1) ^ 1);
     tc_fence_after();
     for (int k = k0; k < k1; ++k) {
@@ -260,7 +261,8 @@ __device__ __forceinline__ void role_epilogue(const ConvParams& p, const Pipe& p
     const int64_t group = v / p.ksplit;
     float* out_part = p.out + (v % p.ksplit) * p.n_out * p.out_pitch;    // this split's partial output
     const int64_t rem = pl.num_tiles - group * pl.T;
-    const int t_eff = rem < pl.T ? (int)rem : pl.T;
+    const int t_eff = pl.T;        // the last group is padded to T tiles (rows >= n_out: never gathered, never stored)
+    (void)rem;
     mbar_wait(smem_u32(pl.tfull + buf), (it >> 1) & 1);
     tc_fence_after();
     for (int t = 0; t < t_eff; ++t) {
@@ -412,7 +414,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
         it.k = (int)(v % p.ksplit) * p.kchunk;
         it.k1 = it.k + p.kchunk < p.K ? it.k + p.kchunk : p.K;
         const int64_t rem = num_tiles - it.group * T;
-        it.t_eff = rem < T ? (int)rem : T;
+        it.t_eff = T;              // padded to T tiles (see role_mma)
+        (void)rem;
       }
     };
     auto advance = [&](SlotIt& it) {
@@ -439,8 +442,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
       }
       if (v < num_items) {
         const int64_t g = v / p.ksplit;
-        const int64_t rem = num_tiles - g * T;
-        prefetch_idx(g, k, gk, rem < T ? (int)rem : T);
+        prefetch_idx(g, k, gk, T);
       } else {
         cp_async_commit();  // keep the group count uniform
       }
@@ -616,7 +618,13 @@ __global__ void __launch_bounds__(NUM_THREADS_PL, 1) k_conv_pl(const __grid_cons
   const int64_t num_groups = (num_tiles + T - 1) / T;
   const int acc_cols = T * p.Cout;
 
-  const int n_mma = T < PL_MMA_WARPS ? T : PL_MMA_WARPS;          // active issuers: one per tile of a group, at most 4
+  // active issuers.  A parity wait is only sound for a waiter that sees EVERY phase of the barrier, so a stage of the A ring
+  // must always be consumed by the same issuer: slot n holds tile n % T (groups are padded to T tiles) and sits in stage
+  // n % sa, hence n_mma must divide both T and sa.  (4 issuers on a 6-stage ring gave rare wrong tiles: an issuer came
+  // back to a stage two fills later and its parity wait passed one fill early.)
+  int n_mma = 1;
+  for (int c = 2; c <= PL_MMA_WARPS && c <= p.pl_depth; c <<= 1)
+    if (T % c == 0 && p.sa % c == 0) n_mma = c;
   if (stat_acc)
     for (int i = threadIdx.x; i < 2 * p.Cout; i += NUM_THREADS_PL) stat_acc[i] = 0.0;
   if (threadIdx.x == 0) {
@@ -669,7 +677,8 @@ __global__ void __launch_bounds__(NUM_THREADS_PL, 1) k_conv_pl(const __grid_cons
         it.k = (int)(v % p.ksplit) * p.kchunk;
         it.k1 = it.k + p.kchunk < p.K ? it.k + p.kchunk : p.K;
         const int64_t rem = num_tiles - it.group * T;
-        it.t_eff = rem < T ? (int)rem : T;
+        it.t_eff = T;              // padded to T tiles (see role_mma)
+        (void)rem;
       }
     };
     auto advance = [&](It& it) {
@@ -944,6 +953,8 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   int sb = 2;
   int sa = (smem_optin - fixed - sb * b_stage) / a_stage;
   if (sa > MAX_STAGES) sa = MAX_STAGES;
+  static const int sa_env = [] { const char* e = getenv("PASCO_PL_SA"); return e ? atoi(e) : 0; }();
+  if (sa_env >= 2 && sa_env < sa) sa = sa_env;
   PASCO_CHECK_ARG(sa >= 2, "pasco_conv_forward_planes: not enough shared memory (Cout=%d)", Cout);
   ConvParams p;
   p.in = nullptr; p.nbr = nbr; p.wpk = (const uint8_t*)packed_w; p.bias = bias;
@@ -967,8 +978,8 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   }
   p.pl_hi = (const uint16_t*)hi; p.pl_lo = (const uint16_t*)lo; p.pl_pitch = pitch;
   static const int depth_env = [] { const char* e = getenv("PASCO_PL_DEPTH"); return e ? atoi(e) : 0; }();
-  p.pl_depth = sa;                           // informational: the producers may run `sa` slots ahead of the MMA
-  (void)depth_env;
+  p.pl_depth = PL_MMA_WARPS;                 // MMA issuer warps (PASCO_PL_DEPTH=1..4 overrides: debugging)
+  if (depth_env >= 1 && depth_env <= PL_MMA_WARPS) p.pl_depth = depth_env;
   const size_t smem = (size_t)sa * a_stage + (size_t)sb * b_stage + fixed;
   const int64_t groups = (tiles + T - 1) / T;
   const int grid = (int)(groups < num_sms() ? groups : num_sms());

@@ -428,7 +428,12 @@ __global__ void __launch_bounds__(NUM_THREADS_WPL, 1) k_wgrad_pl(const __grid_co
   // MMA issuers: the units of a row tile accumulate into different TMEM columns, so issuer `mid` (one thread of warp
   // 8 + mid) owns the units u ≡ mid (mod n_mma); one issuer alone needs ~100 cycles of descriptor work per tcgen05.mma
   // that executes in 32 (N = 64) and left the tensor pipe at 33 %
-  const int n_mma = nunits < WG_MMA_WARPS ? nunits : WG_MMA_WARPS;
+  // A parity wait is only sound for a waiter that sees every phase of the barrier, so a stage of the unit ring must
+  // always be consumed by the same issuer: unit slot `ord` holds unit ord % nunits and sits in stage ord % stages, hence
+  // n_mma must divide both nunits and stages (the host picks `stages` and the pass split accordingly).
+  int n_mma = 1;
+  for (int c = 2; c <= WG_MMA_WARPS && c <= p.depth; ++c)
+    if (nunits % c == 0 && p.stages % c == 0) n_mma = c;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(full_bar + s), 32);    // one cp.async arrival per lane of the warp that fills the slot
@@ -466,7 +471,12 @@ __global__ void __launch_bounds__(NUM_THREADS_WPL, 1) k_wgrad_pl(const __grid_co
     const uint8_t* in_lo = reinterpret_cast<const uint8_t*>(p.in_lo);
     const uint8_t* gp_hi = reinterpret_cast<const uint8_t*>(p.g_hi);
     const uint8_t* gp_lo = reinterpret_cast<const uint8_t*>(p.g_lo);
-    const int Wu = (NUM_GATHER_WARPS - 1) < p.stages ? (NUM_GATHER_WARPS - 1) : p.stages;
+    // unit producers: Wu = the largest divisor of `stages` that is <= 7, so that warp w always fills the same stages
+    // (w, w + Wu, ...) and sees every phase of their "empty" barriers — with several MMA issuers stages are not freed in
+    // slot order, and a producer that skipped a revolution of a stage could pass its parity wait one use early
+    int Wu = 1;
+    for (int c = 2; c <= NUM_GATHER_WARPS - 1; ++c)
+      if (p.stages % c == 0) Wu = c;
     if (warp == NUM_GATHER_WARPS - 1) {
       // ---- gout tiles: [64 rows][Cout] per plane, contiguous rows ----
       for (int64_t rti = 0; rti < my_rts; ++rti) {
@@ -722,11 +732,36 @@ extern "C" int pasco_conv_wgrad_planes(const void* in_hi, const void* in_lo, int
   if (depth_env > 0 && depth_env < p.depth) p.depth = depth_env;
   p.num_subs = K * (Cin / 64);
   p.num_units = (p.num_subs + 1) / 2;
-  p.units_per_pass = 512 / Cout;
+  const int units_cap = 512 / Cout;                             // accumulators that fit TMEM
+  p.units_per_pass = units_cap;
   if (p.units_per_pass > p.num_units) p.units_per_pass = p.num_units;
   p.tmem_cols = pow2_cols(p.units_per_pass * Cout);
   p.passes = (p.num_units + p.units_per_pass - 1) / p.units_per_pass;
-  p.units_per_pass = (p.num_units + p.passes - 1) / p.passes;   // balance the passes (8+6 → 7+7)
+  p.units_per_pass = (p.num_units + p.passes - 1) / p.passes;   // balance the passes (8+6 → 7+7) ...
+  // ... unless that makes the unit count odd: several MMA issuers need a common divisor of units and stages (kernel
+  // comment), so 14 units run as 8 + 6 rather than 7 + 7
+  if ((p.units_per_pass & 1) && p.units_per_pass + 1 <= units_cap && p.units_per_pass > 1) p.units_per_pass += 1;
+  {
+    static const int nm_env = [] { const char* e = getenv("PASCO_WG_NM"); return e ? atoi(e) : 0; }();
+    const int nm_max = nm_env >= 1 && nm_env <= WG_MMA_WARPS ? nm_env : WG_MMA_WARPS;
+    int best = 1;
+    for (int c = 2; c <= nm_max; ++c)
+      if (p.units_per_pass % c == 0 && stages / c >= 1 && (stages / c) * c >= 2) best = c;
+    // stages: a multiple of the issuer count, and with a large divisor <= 7 (= the number of producer warps, see kernel)
+    {
+      int pick = 0, pick_w = 0;
+      for (int st = stages; st >= 2; --st) {
+        if (st % best) continue;
+        int w = 1;
+        for (int c = 2; c <= 7; ++c)
+          if (st % c == 0) w = c;
+        if (w > pick_w) { pick_w = w; pick = st; }
+      }
+      if (pick) stages = pick;
+    }
+    p.stages = stages;
+    p.depth = nm_max;                                           // most issuers a CTA may use
+  }
   const int64_t num_rt = (n_out + WG_R - 1) / WG_R;
   int cpp = num_sms() / p.passes;
   if (cpp < 1) cpp = 1;

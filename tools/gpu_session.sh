@@ -11,7 +11,7 @@ for S in $STEPS; do
     dbg)
       timeout 150 python tools/debug_planes.py > $O/${TAG}_dbg.log 2>&1; rc=$?
       grep -c "equal: True" $O/${TAG}_dbg.log; grep "False\|Error\|error" $O/${TAG}_dbg.log | head -5
-      if [ $rc -ne 0 ]; then echo "debug step failed/hung (rc=$rc): stopping"; tail -5 $O/${TAG}_dbg.log; exit 1; fi ;;
+      if [ $rc -ne 0 ] || grep -q "False" $O/${TAG}_dbg.log; then echo "debug step failed/hung/mismatch (rc=$rc): stopping"; tail -5 $O/${TAG}_dbg.log; exit 1; fi ;;
     trap)
       PASCO_NVCC_FLAGS=-DPASCO_HANG_TRAP python -m pasco_b200.build --force > $O/${TAG}_trapbuild.log 2>&1
       timeout 200 python tools/debug_planes.py wgrad > $O/${TAG}_trap.log 2>&1
