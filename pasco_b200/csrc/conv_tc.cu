@@ -953,6 +953,9 @@ extern "C" int pasco_conv_forward_planes(const void* hi, const void* lo, int64_t
   int sb = 2;
   int sa = (smem_optin - fixed - sb * b_stage) / a_stage;
   if (sa > MAX_STAGES) sa = MAX_STAGES;
+  // an even ring lets two MMA issuers share the tile groups (n_mma must divide T and sa, see k_conv_pl): at C = 128 in
+  // fp32 mode 4 stages + 2 issuers beat 5 stages + 1 issuer
+  if (T >= 2 && (sa & 1) && sa > 2) sa -= 1;
   static const int sa_env = [] { const char* e = getenv("PASCO_PL_SA"); return e ? atoi(e) : 0; }();
   if (sa_env >= 2 && sa_env < sa) sa = sa_env;
   PASCO_CHECK_ARG(sa >= 2, "pasco_conv_forward_planes: not enough shared memory (Cout=%d)", Cout);
