@@ -179,6 +179,10 @@ __device__ __forceinline__ void role_weight_loader(const ConvParams& p, const Pi
 // The "B stage free" and "accumulators ready" barriers expect one commit per issuer.
 template <int NSPLIT, bool CPASYNC_A = false>
 __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl, int mid = 0, int nm = 1) {
+  // Called by a WHOLE warp: waits, counters and descriptor arithmetic are warp-uniform (the compiler keeps them in uniform
+  // registers), only tcgen05.mma / tcgen05.commit are issued by the elected lane.  (With the loop inside `if (lane == 0)`
+  // every descriptor went through ELECT + R2UR moves: ~13 instructions and ~100 cycles per 32-cycle MMA.)
+  const bool lead = elect_one();
   const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.Cout, 0, 0);
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;
@@ -203,34 +207,38 @@ __device__ __forceinline__ void role_mma(const ConvParams& p, const Pipe& pl, in
           tc_fence_after();
           const uint32_t a_hi = smem_u32(pl.a_smem + (size_t)sa * pl.a_stage_bytes), a_lo = a_hi + A_TILE_BYTES;
           const uint32_t d_tmem = pl.tmem_base + (uint32_t)(buf * pl.acc_cols + t * p.Cout);
+          // descriptors of the k-step j: the start-address field (bits 0-13, 16-byte units) advances by 2 per 32 bytes
+          const uint64_t da_hi0 = make_desc_sw128(a_hi, 16, 1024), db_hi0 = make_desc_sw128(b_hi, 16, 1024);
+          const uint64_t da_lo0 = make_desc_sw128(a_lo, 16, 1024), db_lo0 = make_desc_sw128(b_lo, 16, 1024);
+          if (lead) {
 #pragma unroll
-          for (int j = 0; j < KBLK / 16; ++j) {
-            const uint32_t accum = (k > k0 || kb > 0 || j > 0) ? 1u : 0u;
-            const uint64_t da_hi = make_desc_sw128(a_hi + j * 32, 16, 1024);
-            const uint64_t db_hi = make_desc_sw128(b_hi + j * 32, 16, 1024);
-            mma_bf16(d_tmem, da_hi, db_hi, idesc, accum);
-            if (NSPLIT == 3) {
-              const uint64_t da_lo = make_desc_sw128(a_lo + j * 32, 16, 1024);
-              const uint64_t db_lo = make_desc_sw128(b_lo + j * 32, 16, 1024);
-              mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
-              mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+            for (int j = 0; j < KBLK / 16; ++j) {
+              const uint32_t accum = (k > k0 || kb > 0 || j > 0) ? 1u : 0u;
+              mma_bf16(d_tmem, da_hi0 + 2 * j, db_hi0 + 2 * j, idesc, accum);
+              if (NSPLIT == 3) {
+                mma_bf16(d_tmem, da_lo0 + 2 * j, db_hi0 + 2 * j, idesc, 1);
+                mma_bf16(d_tmem, da_hi0 + 2 * j, db_lo0 + 2 * j, idesc, 1);
+              }
             }
+            mma_commit(smem_u32(pl.aempty + sa));
           }
-          mma_commit(smem_u32(pl.aempty + sa));
+          __syncwarp();
           }
           if (++sa == p.sa) {
             sa = 0;
             pa ^= 1;
           }
         }
-        mma_commit(smem_u32(pl.bempty + sb));
+        if (lead) mma_commit(smem_u32(pl.bempty + sb));
+        __syncwarp();
         if (++sb == p.sb) {
           sb = 0;
           pb ^= 1;
         }
       }
     }
-    mma_commit(smem_u32(pl.tfull + buf));
+    if (lead) mma_commit(smem_u32(pl.tfull + buf));
+    __syncwarp();
   }
 }
 
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
   } else if (warp == LOAD_WARP) {
     if (lane == 0) role_weight_loader(p, pl);
   } else if (warp == MMA_WARP) {
-    if (lane == 0) role_mma<NSPLIT>(p, pl);
+    role_mma<NSPLIT>(p, pl);
   } else {
     role_epilogue(p, pl, warp - NUM_GATHER_WARPS, lane);   // == warp % 4: the TMEM lane quadrant this warp may read
   }
@@ -764,10 +772,10 @@ __global__ void __launch_bounds__(NUM_THREADS_PL, 1) k_conv_pl(const __grid_cons
   } else if (warp == LOAD_WARP) {
     if (lane == 0) role_weight_loader(p, pl);
   } else if (warp == MMA_WARP) {
-    if (lane == 0) role_mma<NSPLIT, true>(p, pl, 0, n_mma);
+    role_mma<NSPLIT, true>(p, pl, 0, n_mma);
   } else if (warp >= PL_MMA_WARP0) {
     const int mid = warp - PL_MMA_WARP0 + 1;
-    if (lane == 0 && mid < n_mma) role_mma<NSPLIT, true>(p, pl, mid, n_mma);
+    if (mid < n_mma) role_mma<NSPLIT, true>(p, pl, mid, n_mma);
   } else {
     role_epilogue(p, pl, warp - NUM_GATHER_WARPS, lane);
   }

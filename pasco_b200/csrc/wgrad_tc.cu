@@ -581,8 +581,11 @@ __global__ void __launch_bounds__(NUM_THREADS_WPL, 1) k_wgrad_pl(const __grid_co
       }
     }
   } else if (warp >= MMA_WARP && warp - MMA_WARP < n_mma) {
+    // whole warp, warp-uniform loop; the elected lane issues tcgen05.mma / tcgen05.commit (descriptors stay in uniform
+    // registers instead of ~13 ELECT / R2UR instructions per MMA)
     const int mid = warp - MMA_WARP;
-    if (lane == 0) {
+    const bool lead = elect_one();
+    {
       const uint32_t idesc = make_idesc_bf16(128, p.Cout, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -594,37 +597,40 @@ __global__ void __launch_bounds__(NUM_THREADS_WPL, 1) k_wgrad_pl(const __grid_co
         tc_fence_after();
         const uint32_t g_hi = smem_u32(g_smem + (size_t)gb * g_bytes);
         const uint32_t g_lo = g_hi + NB * WG_SUB_BYTES;
+        const uint64_t db_hi0 = make_desc_sw128(g_hi, WG_SUB_BYTES, 1024), db_lo0 = make_desc_sw128(g_lo, WG_SUB_BYTES, 1024);
         for (int u = 0; u < nunits; ++u) {
           if (u % n_mma == mid) {
-          mbar_wait(smem_u32(full_bar + stage), phase);
-          fence_proxy_async_smem();
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_smem + (size_t)stage * a_bytes);
-          const uint32_t a_lo = a_hi + 2 * WG_SUB_BYTES;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.Cout);
+            mbar_wait(smem_u32(full_bar + stage), phase);
+            fence_proxy_async_smem();
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(a_smem + (size_t)stage * a_bytes);
+            const uint32_t a_lo = a_hi + 2 * WG_SUB_BYTES;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(u * p.Cout);
+            const uint64_t da_hi0 = make_desc_sw128(a_hi, WG_SUB_BYTES, 1024), da_lo0 = make_desc_sw128(a_lo, WG_SUB_BYTES, 1024);
+            if (lead) {
 #pragma unroll
-          for (int j = 0; j < WG_R / 16; ++j) {
-            const uint32_t acc = (git > 0 || j > 0) ? 1u : 0u;
-            const uint64_t da_hi = make_desc_sw128(a_hi + j * 2048, WG_SUB_BYTES, 1024);
-            const uint64_t db_hi = make_desc_sw128(g_hi + j * 2048, WG_SUB_BYTES, 1024);
-            mma_bf16(d_tmem, da_hi, db_hi, idesc, acc);
-            if (NSPLIT == 3) {
-              const uint64_t da_lo = make_desc_sw128(a_lo + j * 2048, WG_SUB_BYTES, 1024);
-              const uint64_t db_lo = make_desc_sw128(g_lo + j * 2048, WG_SUB_BYTES, 1024);
-              mma_bf16(d_tmem, da_lo, db_hi, idesc, 1);
-              mma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+              for (int j = 0; j < WG_R / 16; ++j) {             // 16 rows = 2048 bytes = 128 address units per k-step
+                const uint32_t acc = (git > 0 || j > 0) ? 1u : 0u;
+                mma_bf16(d_tmem, da_hi0 + 128 * j, db_hi0 + 128 * j, idesc, acc);
+                if (NSPLIT == 3) {
+                  mma_bf16(d_tmem, da_lo0 + 128 * j, db_hi0 + 128 * j, idesc, 1);
+                  mma_bf16(d_tmem, da_hi0 + 128 * j, db_lo0 + 128 * j, idesc, 1);
+                }
+              }
+              mma_commit(smem_u32(empty_bar + stage));
             }
-          }
-          mma_commit(smem_u32(empty_bar + stage));
+            __syncwarp();
           }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        mma_commit(smem_u32(gempty_bar + gb));
+        if (lead) mma_commit(smem_u32(gempty_bar + gb));
+        __syncwarp();
       }
-      mma_commit(smem_u32(done_bar));
+      if (lead) mma_commit(smem_u32(done_bar));
+      __syncwarp();
     }
   }
   tc_fence_before();

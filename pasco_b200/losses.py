@@ -73,7 +73,18 @@ def hungarian(query_logits, mask_logits, tgt_cls, tgt_masks, w_class=1.0, w_mask
     """query_logits [Q,K+1], mask_logits [P,Q], tgt_masks [T,P] → (query idx, target idx).  CPU crossing
     exactly where the reference has one (matcher_sparse.py:151)."""
     prob = query_logits.softmax(-1)
-    out = mask_logits.t()                                           # [Q,P]
+    out = mask_logits.t().float()                                   # [Q,P]
+    # the three [Q,P]x[P,T] cost GEMMs only rank assignments: TF32 is allowed here even in the fp32 parity mode (the fp32
+    # CUDA-core library GEMMs took 3 ms per step for 0.8 GFLOP because of the P = 400 k reduction dimension)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        return _hungarian_costs(prob, out, tgt_cls, tgt_masks.float(), w_class, w_mask, w_dice)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def _hungarian_costs(prob, out, tgt_cls, tgt_masks, w_class, w_mask, w_dice):
     cost_class = -prob[:, tgt_cls]
     sig = out.sigmoid()
     num = 2 * sig @ tgt_masks.t()

@@ -17,6 +17,8 @@ for S in $STEPS; do
       timeout 200 python tools/debug_planes.py wgrad > $O/${TAG}_trap.log 2>&1
       grep "HANG" $O/${TAG}_trap.log | sort | uniq -c | sort -rn | head -40; tail -5 $O/${TAG}_trap.log | cut -c1-300
       python -m pasco_b200.build --force > /dev/null 2>&1 ;;
+    profile)
+      timeout 300 python tools/profile_step.py --out $O/${TAG}_profile.txt 2>&1 | tail -2; head -45 $O/${TAG}_profile.txt | cut -c1-200 ;;
     micro)
       timeout 200 python tools/conv_microbench.py --occ 0.5 0.1 --channels 64 128 256 --out $O/${TAG}_micro.jsonl 2>&1 | grep conv3 | python -c "
 import sys, json
