@@ -24,7 +24,7 @@ for S in $STEPS; do
 import sys, json
 for l in sys.stdin:
     d = json.loads(l)
-    print(d['N'], d['C'], d['precision'], {k: round(v, 3) for k, v in d.items() if k.endswith('_ms')})" ;;
+    if "precision" in d: print(d["N"], d["C"], d["precision"], {k: round(v, 3) for k, v in d.items() if k.endswith('_ms')})" ;;
     ops)
       timeout 400 python -m pytest tests/test_gpu_ops.py -x -q -m gpu > $O/${TAG}_ops.log 2>&1; tail -4 $O/${TAG}_ops.log ;;
     golden)
