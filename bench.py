@@ -47,7 +47,7 @@ def log(msg):
         print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 GRID, OCC, IN_CH, N_CLASSES = (256, 256, 32), 0.10, 283, 20
-SETTLE = 2          # extra untimed steps right before the first timed region (on top of --warmup)
+SETTLE = 4          # extra untimed steps right before the first timed region (on top of --warmup)
 METRIC = "scenes/sec (256x256x32 voxels @10% occ) fwd+bwd"
 # --shape: the two dataset shapes of BASELINE.json's configs (SemanticKITTI: net_panoptic_sparse.py:51; KITTI-360:
 # train_kitti360.py:115,152 — 19 classes, 8-wide point features, 8 % occupancy in configs[4])
@@ -85,11 +85,7 @@ def _ncu_traffic(kind, meta):
         want = _kernel_name(kind, meta)
         for k in d["kernels"]:
             if want in k["kernel"]:
-                tot = 0.0
-                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    v, u = k[key].split()
-                    tot += float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[u]
-                return tot
+                return float(k["dram_bytes_per_launch"])
     except Exception:
         pass
     return None

@@ -41,6 +41,11 @@ for l in sys.stdin:
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 14000 -c 6000 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/${TAG}_launches.log 2>&1; wc -l $O/${TAG}_launches.csv ;;
     ncu_hbm)
-      timeout 700 ncu --set full --clock-control none -k regex:'k_col_sums|k_bn_bwd|k_affine_act|k_split_planes|k_gather_rows|k_scatter_rows|k_kernel_map|k_hash|k_mask|k_xattn|k_maxpool|k_scatter_max|k_dense|k_pack' -s 2500 -c 60 -o $O/${TAG}_hbm python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_hbm.log 2>&1; ls -la $O/${TAG}_hbm.ncu-rep ;;
+      # HBM-bound kernels of one bench step: slim section set, summarised ON THE BOX (the .ncu-rep stays in /tmp: gpurun merges
+      # at most 64 MiB back)
+      timeout 500 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section WarpStateStats --section Occupancy \
+        --clock-control none -k regex:'k_col_sums|k_bn_bwd|k_affine_act|k_split_planes|k_gather_rows|k_scatter_rows|k_kernel_map|k_hash|k_mask|k_xattn|k_maxpool|k_scatter_max|k_dense|k_pack|k_bn_finalize' \
+        -s 1300 -c 45 -o /tmp/${TAG}_hbm python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_hbm.log 2>&1
+      python tools/ncu_summarise.py /tmp/${TAG}_hbm.ncu-rep --out $O/${TAG}_ncu_hbm.json --note "one bench step (configs[1] shape, fp32 mode), 45 launches of the non-convolution kernels" | head -30 ;;
   esac
 done
