@@ -47,7 +47,7 @@ def log(msg):
         print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 GRID, OCC, IN_CH, N_CLASSES = (256, 256, 32), 0.10, 283, 20
-SETTLE = 4          # extra untimed steps right before the first timed region (on top of --warmup)
+SETTLE = 8          # extra untimed steps right before the first timed region (on top of --warmup): twice through the scene pool
 METRIC = "scenes/sec (256x256x32 voxels @10% occ) fwd+bwd"
 # --shape: the two dataset shapes of BASELINE.json's configs (SemanticKITTI: net_panoptic_sparse.py:51; KITTI-360:
 # train_kitti360.py:115,152 — 19 classes, 8-wide point features, 8 % occupancy in configs[4])
