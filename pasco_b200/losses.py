@@ -107,12 +107,15 @@ def panoptic_set_loss(pred: Dict, tgt_cls: torch.Tensor, tgt_masks: torch.Tensor
     dev = levels[0][0].device
     qi, tj = hungarian(levels[0][0][0], levels[0][1], tgt_cls, tgt_masks)
     qi, tj = qi.to(dev), tj.to(dev)
-    empty_w = torch.ones(n_classes + 1, device=dev)
+    # the class head always has 20 + 1 outputs (the reference builds TransformerPredictor without num_classes), the last one
+    # being "no object" — also for KITTI-360's 19 classes
+    n_logits = levels[0][0].shape[-1]
+    empty_w = torch.ones(n_logits, device=dev)
     empty_w[-1] = eos_coef
     total = 0.0
     for qlog, mlog in levels:
         q = qlog[0]
-        target_cls = torch.full((q.shape[0],), n_classes, dtype=torch.int64, device=dev)
+        target_cls = torch.full((q.shape[0],), n_logits - 1, dtype=torch.int64, device=dev)
         target_cls[qi] = tgt_cls[tj]
         l_ce = F.cross_entropy(q, target_cls, empty_w)
         src = mlog.t()[qi]                                          # [T',P]
