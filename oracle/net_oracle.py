@@ -223,8 +223,7 @@ def time_crop(repeats: int = 3, warmup: int = 1, occ=0.10, grid=CROP_GRID, div=C
     bench.py's cpu_baseline leg and for --impl reference): `warmup` untimed passes, then `repeats` timed passes.
     Returns the median time, the spread and scenes/s scaled to a full scene under the stated assumption that the cost is
     linear in the voxel count (the crop keeps the occupancy, the z extent and the cap-to-voxel ratio of the full scene)."""
-    from pasco_b200.synthetic import make_scene
-    from pasco_b200.losses import total_loss
+    from scene_and_loss import make_scene, total_loss       # the oracle's own copy: nothing of the product on this arm
     torch.manual_seed(0)
     net = OracleNet(caps=tuple(max(8, c // div) for c in (25000, 120000, 400000))).train()
     scene = make_scene(grid, occ, 1, seed=0)

@@ -46,3 +46,27 @@ def test_masks_at_matches_box_membership():
     boxes = [((0, 0, 0), (10, 10, 10)), ((5, 5, 5), (30, 20, 11))]
     m = losses.masks_at(c, boxes)
     assert m.tolist() == [[1.0, 1.0, 0.0, 0.0], [0.0, 1.0, 0.0, 1.0]]
+
+
+def test_oracle_copy_of_scene_and_losses_agrees_with_the_product():
+    """oracle/scene_and_loss.py (the CPU arm's own copy, so that `bench.py --impl reference` imports nothing from the
+    product) produces the same scene and the same loss pieces as pasco_b200.synthetic / pasco_b200.losses."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import scene_and_loss as OS
+    from pasco_b200.synthetic import make_scene
+    a, b = make_scene((32, 32, 8), 0.1, 1, seed=3), OS.make_scene((32, 32, 8), 0.1, 1, seed=3)
+    assert torch.equal(a["in_coords"][0], b["in_coords"][0]) and torch.equal(a["in_feats"][0], b["in_feats"][0])
+    assert all(torch.equal(a["sem_labels"][k], b["sem_labels"][k]) for k in a["sem_labels"]) and a["mask_boxes"] == b["mask_boxes"]
+    g = torch.Generator().manual_seed(1)
+    logits, labels = torch.randn(500, 20, generator=g, dtype=torch.float64), torch.randint(0, 20, (500,), generator=g)
+    assert float(losses.lovasz_softmax_present(F.softmax(logits, 1), labels)) == float(OS.lovasz_softmax_present(F.softmax(logits, 1), labels))
+    q, m = torch.randn(1, 30, 21, generator=g), torch.randn(400, 30, generator=g)
+    tc, tm = torch.randint(1, 20, (6,), generator=g), (torch.rand(6, 400, generator=g) > 0.7).float()
+
+    class _V:
+        def __init__(self, f):
+            self.F = f
+    pred = {"query_logits": q, "voxel_logits": _V(m), "aux_outputs": []}
+    assert abs(float(losses.panoptic_set_loss(pred, tc, tm, 20)) - float(OS.panoptic_set_loss(pred, tc, tm, 20))) < 1e-6
