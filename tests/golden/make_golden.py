@@ -71,36 +71,5 @@ def main():
     make(2, "cfg1_m2", 32)
 
 
-def _old_main():
-
-    torch.set_num_threads(os.cpu_count())
-    net = build_net(1, 64)
-    sd = net.state_dict()
-    net.load_state_dict(fill_state_dict(sd))
-    net.train()
-    batch = make_scene(GRID, OCC, 1, seed=SEED)
-    with torch.no_grad():
-        _, out = forward(net, batch)
-    arrays = {}
-    manifest = {k: list(v.shape) for k, v in sd.items()
-                if not k.startswith(("unet3d.transformer_predictor.", "unet3d.decoder_generative.transformer_predictor.",
-                                     "criterion."))}
-    for s, lg in out["sem_logits_at_scales"].items():
-        c, f = canon(lg[0])
-        arrays[f"sem{s}_C"], arrays[f"sem{s}_F"] = c, f[::STEP]
-        arrays[f"sem{s}_sum"] = np.array([f.sum(dtype=np.float64), np.abs(f).sum(dtype=np.float64)])
-    p = out["panop_predictions"][0]
-    arrays["query_logits"] = p["query_logits"][0].numpy()
-    c, f = canon(p["voxel_logits"])
-    arrays["vox_C"], arrays["vox_F"] = c, f[::STEP]
-    arrays["vox_sum"] = np.array([f.sum(dtype=np.float64), np.abs(f).sum(dtype=np.float64)])
-    for i, aux in enumerate(p["aux_outputs"]):
-        arrays[f"aux{i}_query_logits"] = aux["query_logits"][0].numpy()
-    np.savez_compressed(os.path.join(HERE, "net_cfg1.npz"), **arrays)
-    json.dump({"grid": GRID, "occ": OCC, "seed": SEED, "row_step": STEP, "params": manifest},
-              open(os.path.join(HERE, "net_cfg1_manifest.json"), "w"), indent=0)
-    print({k: v.shape for k, v in arrays.items()})
-
-
 if __name__ == "__main__":
     main()
