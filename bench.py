@@ -450,7 +450,8 @@ def run_reference(a):
                                    "step time), assuming cost linear in voxels",
                        "parallelism": f"cpu x{cores} threads", "scene_fraction_per_step": 1.0 / r["div"]},
             "cpu_baseline": {"value": round(v, 6), "unit": "scenes/s", "cores": cores, "kind": "port",
-                             "sample": r["sample"], "times": r["times"], "spread": r["spread"]},
+                             "sample": r["sample"].replace("0 warm-up +", f"{n_warm} warm-up + 1 probe pass (untimed) +"),
+                             "times": r["times"], "spread": r["spread"]},
             "e2e": {"value": round(v, 6), "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if a.ref_full_scene:
         f = net_oracle.time_full_scene()
