@@ -198,10 +198,12 @@ class Trainer:
             opts, scheds = cfg
             self.optimizers = list(opts)
             self.lr_schedulers = [s["scheduler"] if isinstance(s, dict) else s for s in scheds]
+            self._sched_interval = [s.get("interval", "epoch") if isinstance(s, dict) else "epoch" for s in scheds]
         elif isinstance(cfg, dict):
             self.optimizers = [cfg["optimizer"]]
             s = cfg.get("lr_scheduler")
             self.lr_schedulers = [s["scheduler"] if isinstance(s, dict) else s] if s else []
+            self._sched_interval = [s.get("interval", "epoch") if isinstance(s, dict) else "epoch"] if s else []
         else:
             self.optimizers = [cfg]
 
@@ -232,6 +234,13 @@ class Trainer:
                 sc.load_state_dict(s)
             self.current_epoch, self.global_step = ck.get("epoch", 0) + 1, ck.get("global_step", 0)
         opt = self.optimizers[0]
+        # world > 1: the reference's DDP(find_unused_parameters=True) (scripts/train.py:213) = pasco_b200's bucketed reducer:
+        # gradients are views into one flat buffer, buckets are all-reduced from backward hooks while backward still runs
+        reducer = None
+        if self.world_size > 1:
+            from pasco_b200.parallel import GradReducer
+            reducer = GradReducer(list(model.parameters()))
+        A = self.accumulate_grad_batches
         for epoch in range(self.current_epoch, self.max_epochs):
             self.current_epoch = epoch
             model.train()
@@ -240,22 +249,33 @@ class Trainer:
                 if i >= n:
                     break
                 batch = _to_device(batch, self.device)
+                last = (i + 1) % A == 0
+                if reducer is not None:
+                    reducer.rearm(sync=last)        # only the last micro-step of an optimiser step launches the all-reduces
                 out = model.training_step(batch, i)
                 loss = out["loss"] if isinstance(out, dict) else out
-                (loss / self.accumulate_grad_batches).backward()
-                if (i + 1) % self.accumulate_grad_batches == 0:
-                    if self.world_size > 1:
-                        _allreduce_grads(model, self.world_size)
+                (loss / A).backward()
+                if last:
+                    if reducer is not None:
+                        reducer.finish()
                     if self.gradient_clip_val:
                         torch.nn.utils.clip_grad_norm_(model.parameters(), self.gradient_clip_val)
                     opt.step()
-                    opt.zero_grad(set_to_none=True)
+                    if reducer is not None:
+                        reducer.zero_grad()         # one memset; the gradients stay views into the flat buffer
+                    else:
+                        opt.zero_grad(set_to_none=True)
                     self.global_step += 1
+            for sc, iv in zip(self.lr_schedulers, getattr(self, "_sched_interval", [])):
+                if iv == "epoch":                   # Lightning steps an {"interval": "epoch"} scheduler once per epoch
+                    sc.step()                       # (net_panoptic_sparse.py:901; the model also steps it per batch, :768-770)
             if val_dataloaders is not None and (epoch + 1) % self.check_val_every_n_epoch == 0:
                 self._eval_loop(model, val_dataloaders, "val")
             for cb in self.callbacks:
                 if hasattr(cb, "on_train_epoch_end"):
                     cb.on_train_epoch_end(self, model)
+        if reducer is not None:
+            reducer.detach()
         return model
 
     def _eval_loop(self, model, loader, kind):
@@ -286,17 +306,3 @@ class Trainer:
             datamodule.setup("test")
             dataloaders = datamodule.test_dataloader()
         return self._eval_loop(model, dataloaders, "test")
-
-
-def _allreduce_grads(model, world_size):
-    """One flat NCCL all-reduce of all gradients (the reference's DDP bucket all-reduce,
-    scripts/train.py:213; parameters without grad contribute zeros = find_unused_parameters)."""
-    params = [p for p in model.parameters() if p.requires_grad]
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
-    dist.all_reduce(flat)
-    flat /= world_size
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.grad = flat[off:off + n].view_as(p).clone()
-        off += n
