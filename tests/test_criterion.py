@@ -121,9 +121,8 @@ def test_degenerate_inputs():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: first run on a CUDA device; the "
-                                        "CPU tests above are the strict ones (same code, device-agnostic torch ops)")
 def test_criterion_on_the_device_matches_reference(gold):
+    """Same fixture on cuda:0 (first run: profiles/r02_criterion_gpu.log)."""
     dev = torch.device("cuda:0")
     out, batch, freqs, crit, leaves = _inputs(gold, grad=True)
 
