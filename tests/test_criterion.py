@@ -137,7 +137,12 @@ def test_criterion_on_the_device_matches_reference(gold):
             return [mv(v) for v in x]
         return x
     out_d, batch_d = mv(out), mv(batch)
-    total, terms = CR.training_loss(out_d, batch_d, crit, freqs)
+    tf32 = torch.backends.cuda.matmul.allow_tf32       # whatever an earlier test left behind: the comparison is fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        total, terms = CR.training_loss(out_d, batch_d, crit, freqs)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
     assert _close(total, gold["total"], 1e-4), (float(total), float(gold["total"]))
     total.backward()
     g = out_d["panop_predictions"][0]["voxel_logits"].F.grad.cpu()
