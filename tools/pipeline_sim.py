@@ -58,6 +58,17 @@ def sim(Wu, nunits, stages, nm, rts, seed):
         idle=0 if after!=before else idle+1
         if idle>30000: return 'DEADLOCK'
     return 'ERR' if err else 'ok'
-for (Wu,nunits,stages,nm) in ((7,8,8,2),(4,8,8,2),(4,8,8,4),(6,8,6,2),(6,6,6,3),(4,4,4,4),(5,4,5,1),(7,7,8,1),(2,2,2,2),(6,8,6,4)):
-    res=[sim(Wu,nunits,stages,nm,14,s) for s in range(80)]
-    print((Wu,nunits,stages,nm), {k:res.count(k) for k in set(res)})
+def host_choice(nunits, stages, max_issuers=4, max_producers=7):
+    """The role counts the host code derives from (units per pass, ring stages) — wgrad_tc.cu / conv_tc.cu."""
+    Wu = max(d for d in range(1, max_producers + 1) if stages % d == 0)
+    nm = 1
+    for c in range(2, max_issuers + 1):        # k_wgrad_pl takes any count; k_conv_pl only the powers of two among them
+        if nunits % c == 0 and stages % c == 0:
+            nm = c
+    return Wu, nm
+
+
+if __name__ == "__main__":
+    for (Wu,nunits,stages,nm) in ((7,8,8,2),(4,8,8,2),(4,8,8,4),(6,8,6,2),(6,6,6,3),(4,4,4,4),(5,4,5,1),(7,7,8,1),(2,2,2,2),(6,8,6,4)):
+        res=[sim(Wu,nunits,stages,nm,14,s) for s in range(80)]
+        print((Wu,nunits,stages,nm), {k:res.count(k) for k in set(res)})
